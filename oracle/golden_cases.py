@@ -1,0 +1,50 @@
+"""Golden-vector case table shared by tests/golden/make_golden.py (which runs the
+verbatim reference) and the parity tests (which rebuild the identical inputs and
+weights from the seeds).  TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import torch
+
+from .gotennet_oracle import OracleConfig
+
+CASES = {
+    # BASELINE.json configs[0]: class defaults, C=64, 2 interactions, lmax=1, one 20-atom molecule
+    "cfg1": dict(cfg=OracleConfig(n_atom_basis=64, n_interactions=2, lmax=1), atoms=[20], seed=1),
+    # configs/model/gotennet.yaml flags (lmax=2, sep_* on, scale_edge off) at reduced width,
+    # ragged batch incl. a single-atom and a two-atom molecule
+    "yaml_l2": dict(cfg=OracleConfig(n_atom_basis=64, n_interactions=3, lmax=2, sep_dir=True,
+                                     sep_tensor=True, scale_edge=False),
+                    atoms=[17, 1, 23, 2, 9], seed=2),
+    # lmax=3 with neighbour truncation (asymmetric graph)
+    "l3_trunc": dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=3, num_heads=4, sep_dir=True,
+                                      sep_tensor=True, scale_edge=True, max_num_neighbors=8),
+                     atoms=[40, 5], seed=3),
+    # all sep_* off at lmax=2 (shared W_vk, single direction / tensor chunk)
+    "nosep_l2": dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, sep_htr=False,
+                                      sep_dir=False, sep_tensor=False, scale_edge=True),
+                     atoms=[12, 14], seed=4),
+}
+
+
+def blob(n_atoms, seed, sigma0=1.45):
+    """Gaussian-blob molecules of the given sizes: z [N] i64, pos [N,3] f32, batch [N] i64."""
+    g = torch.Generator().manual_seed(seed)
+    sizes = torch.tensor(n_atoms)
+    batch = torch.repeat_interleave(torch.arange(len(n_atoms)), sizes)
+    sigma = sigma0 * (sizes.double() / 18.0).pow(1 / 3).float()
+    pos = torch.randn(int(sizes.sum()), 3, generator=g) * sigma[batch].unsqueeze(-1)
+    species = torch.tensor([1, 6, 7, 8, 9])
+    z = species[torch.randint(0, 5, (int(sizes.sum()),), generator=g)]
+    return z, pos, batch
+
+
+def probe_vector(n):
+    g = torch.Generator().manual_seed(12345 + n)
+    return torch.randn(n, generator=g)
+
+
+def grad_fingerprint(g):
+    """1-D gradients are kept whole; matrices as a seeded random projection of every row."""
+    if g.dim() == 1:
+        return g
+    return g @ probe_vector(g.shape[1]).to(g.dtype).to(g.device)

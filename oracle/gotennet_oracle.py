@@ -1,0 +1,426 @@
+"""CPU oracle: a plain-PyTorch restatement of the GotenNet interaction stack.
+
+TEST INFRASTRUCTURE ONLY.  The product (gotennet_b200/) never imports this
+module; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+`--impl reference` legs do, and there only as the checker / the timed CPU
+baseline.  The product path fails loudly when the CUDA library is missing.
+
+Parity pin: the reference ships NO tests and NO golden vectors,
+so this restatement is pinned against outputs of the *verbatim reference code*
+executed in the build container under `oracle/ref_standins.py`
+(tests/golden/make_golden.py -> tests/golden/*.npz, and
+tests/test_oracle_vs_reference.py which re-runs the comparison whenever
+/root/reference is present).
+
+Everything is functional: parameters come from a `state_dict` that uses the
+reference's own key names, so a reference checkpoint can be
+fed to the oracle and to the CUDA path unchanged.  All functions are dtype
+generic (float32 for parity, float64 as a tie-breaker) and differentiable with
+torch.autograd (that is the backward oracle).
+
+Citations are `file:line` relative to /root/reference/gotennet/models/.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# --------------------------------------------------------------------------
+# configuration
+# --------------------------------------------------------------------------
+@dataclass
+class OracleConfig:
+    """Constructor surface of GotenNet that changes the arithmetic
+    (representation/gotennet.py:767-793, :1018)."""
+
+    n_atom_basis: int = 128
+    n_interactions: int = 8
+    n_rbf: int = 32
+    cutoff: float = 5.0
+    max_z: int = 100
+    epsilon: float = 1e-8
+    num_heads: int = 8
+    edge_updates: bool = True
+    scale_edge: bool = True
+    lmax: int = 1
+    sep_htr: bool = True
+    sep_dir: bool = False
+    sep_tensor: bool = False
+    max_num_neighbors: int = 32
+
+    @property
+    def L(self) -> int:
+        return (self.lmax + 1) ** 2 - 1
+
+    @property
+    def S(self) -> int:  # gotennet.py:197-203
+        s = 3
+        if self.sep_dir:
+            s += self.lmax - 1
+        if self.sep_tensor:
+            s += self.lmax - 1
+        return s
+
+
+def degree_slices(lmax: int) -> List[Tuple[int, int]]:
+    """[start, stop) of each degree-l block in the L axis (gotennet.py:37-51)."""
+    out, s = [], 0
+    for l in range(1, lmax + 1):
+        out.append((s, s + 2 * l + 1))
+        s += 2 * l + 1
+    return out
+
+
+# --------------------------------------------------------------------------
+# state_dict helpers
+# --------------------------------------------------------------------------
+def state_dict_spec(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]:
+    """(key, shape, kind) for every *unique* tensor, in the reference's
+    registration order.  kind in {weight,bias,ln_w,ln_b,emb,buf}."""
+    C, R, S = cfg.n_atom_basis, cfg.n_rbf, cfg.S
+    sp: List[Tuple[str, Tuple[int, ...], str]] = []
+    sp.append(("node_init.A_nbr.weight", (cfg.max_z, C), "emb"))
+    sp.append(("node_init.W_ndp.dense_layers.0.weight", (C, R), "weight"))
+    sp.append(("node_init.W_ndp.dense_layers.0.bias", (C,), "bias"))
+    sp.append(("node_init.W_nrd_nru.dense_layers.0.weight", (C, 2 * C), "weight"))
+    sp.append(("node_init.W_nrd_nru.dense_layers.0.bias", (C,), "bias"))
+    sp.append(("node_init.W_nrd_nru.dense_layers.0.norm.weight", (C,), "ln_w"))
+    sp.append(("node_init.W_nrd_nru.dense_layers.0.norm.bias", (C,), "ln_b"))
+    sp.append(("node_init.W_nrd_nru.dense_layers.1.weight", (C, C), "weight"))
+    sp.append(("node_init.W_nrd_nru.dense_layers.1.bias", (C,), "bias"))
+    sp.append(("edge_init.W_erp.weight", (C, R), "weight"))
+    sp.append(("edge_init.W_erp.bias", (C,), "bias"))
+    sp.append(("A_na.weight", (cfg.max_z, C), "emb0"))
+    for i in range(cfg.n_interactions):
+        p = f"gata_list.{i}."
+        last = i == cfg.n_interactions - 1
+        for g in ("gamma_s", "gamma_v"):
+            sp.append((p + f"{g}.0.weight", (C, C), "weight"))
+            sp.append((p + f"{g}.0.bias", (C,), "bias"))
+            sp.append((p + f"{g}.1.weight", (S * C, C), "weight"))
+            sp.append((p + f"{g}.1.bias", (S * C,), "bias"))
+        for g in ("W_q", "W_k", "W_re"):
+            sp.append((p + f"{g}.weight", (C, C), "weight"))
+            sp.append((p + f"{g}.bias", (C,), "bias"))
+        sp.append((p + "W_rs.weight", (S * C, C), "weight"))
+        sp.append((p + "W_rs.bias", (S * C,), "bias"))
+        if not last and cfg.edge_updates:
+            sp.append((p + "gamma_t.dense_layers.0.weight", (C, C), "weight"))
+            sp.append((p + "gamma_t.dense_layers.0.bias", (C,), "bias"))
+            sp.append((p + "W_vq.weight", (C, C), "weight"))
+            if cfg.sep_htr:
+                for l in range(cfg.lmax):
+                    sp.append((p + f"W_vk.{l}.weight", (C, C), "weight"))
+            else:
+                sp.append((p + "W_vk.weight", (C, C), "weight"))
+    for i in range(cfg.n_interactions):
+        p = f"eqff_list.{i}."
+        sp.append((p + "gamma_m.0.weight", (C, 2 * C), "weight"))
+        sp.append((p + "gamma_m.0.bias", (C,), "bias"))
+        sp.append((p + "gamma_m.1.weight", (2 * C, C), "weight"))
+        sp.append((p + "gamma_m.1.bias", (2 * C,), "bias"))
+        sp.append((p + "W_vu.weight", (C, C), "weight"))
+    return sp
+
+
+def rbf_buffers(cfg: OracleConfig, dtype=torch.float32) -> Tuple[Tensor, Tensor]:
+    """ExpNormalSmearing._initial_params (components/layers.py:733-737)."""
+    start = torch.exp(torch.scalar_tensor(-cfg.cutoff))
+    means = torch.linspace(start, 1, cfg.n_rbf)
+    betas = torch.tensor([(2 / cfg.n_rbf * (1 - start)) ** -2] * cfg.n_rbf)
+    return means.to(dtype), betas.to(dtype)
+
+
+def make_state_dict(cfg: OracleConfig, seed: int = 0, bias_scale: float = 0.1,
+                    dtype=torch.float32) -> Dict[str, Tensor]:
+    """Deterministic synthetic weights shared by the golden generator, the tests
+    and the benchmark.  Weights are xavier-uniform *shaped* (same bounds as the
+    reference initialiser, layers.py:503-509) but drawn from one seeded CPU
+    generator in spec order, and biases / LayerNorm affine are made NON-trivial
+    (the reference zero-initialises them, which would hide bias bugs)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, Tensor] = {}
+    for key, shape, kind in state_dict_spec(cfg):
+        if kind == "weight":
+            bound = math.sqrt(6.0 / (shape[0] + shape[1]))
+            t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound
+        elif kind == "bias":
+            t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bias_scale
+        elif kind == "ln_w":
+            t = 1.0 + (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bias_scale
+        elif kind == "ln_b":
+            t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bias_scale
+        else:  # embeddings ~ N(0,1); A_na has padding_idx=0 (gotennet.py:856)
+            t = torch.randn(shape, generator=g, dtype=torch.float64)
+            if kind == "emb0":
+                t[0].zero_()
+        sd[key] = t.to(dtype)
+    means, betas = rbf_buffers(cfg, dtype)
+    sd["radial_basis.means"], sd["radial_basis.betas"] = means, betas
+    return sd
+
+
+def expand_aliases(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """MLP registers each Dense under `dense_layers.i` AND `layers.i`
+    (layers.py:566-571): add the aliased duplicate keys the reference expects."""
+    out = dict(sd)
+    for k, v in sd.items():
+        if ".dense_layers." in k:
+            out[k.replace(".dense_layers.", ".layers.")] = v
+    return out
+
+
+# --------------------------------------------------------------------------
+# graph + geometry  (components/layers.py:1566-1604; torch_cluster semantics)
+# --------------------------------------------------------------------------
+def radius_graph(pos: Tensor, batch: Tensor, r: float, max_num_neighbors: int = 32,
+                 loop: bool = True) -> Tensor:
+    """torch_cluster.radius_graph, CUDA-build semantics (call at layers.py:1589):
+    strict d^2 < r^2 in the dtype of `pos`, same molecule only, at most K sources
+    per target kept in ascending source index, output sorted by (target, source).
+    Row 0 = source j, row 1 = target i.  Done per molecule (dense)."""
+    n = pos.size(0)
+    if n == 0:
+        return torch.zeros(2, 0, dtype=torch.long)
+    # molecule boundaries (batch is sorted, PyG convention)
+    change = torch.ones(n, dtype=torch.bool)
+    change[1:] = batch[1:] != batch[:-1]
+    starts = change.nonzero().flatten().tolist() + [n]
+    r2 = torch.tensor(r, dtype=pos.dtype) ** 2
+    srcs, tgts = [], []
+    for a, b in zip(starts[:-1], starts[1:]):
+        p = pos[a:b]
+        d = p.unsqueeze(1) - p.unsqueeze(0)          # [target, source, 3]
+        d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+        ok = d2 < r2
+        if not loop:
+            ok &= ~torch.eye(b - a, dtype=torch.bool)
+        ok &= ok.long().cumsum(1) <= max_num_neighbors
+        t, s = ok.nonzero(as_tuple=True)
+        srcs.append(s + a)
+        tgts.append(t + a)
+    return torch.stack([torch.cat(srcs), torch.cat(tgts)], 0)
+
+
+def edge_geometry(pos: Tensor, edge_index: Tensor) -> Tuple[Tensor, Tensor]:
+    """Distance.forward (layers.py:1591-1604): edge_vec = pos[src] - pos[tgt];
+    edge_weight = |edge_vec| on non-loop edges, exactly 0 on self loops."""
+    src, tgt = edge_index[0], edge_index[1]
+    vec = pos[src] - pos[tgt]
+    mask = src != tgt
+    # norm only where it is differentiable (self-loop rows stay 0, as the
+    # reference's masked assignment does)
+    safe = torch.where(mask.unsqueeze(-1), vec, torch.ones_like(vec))
+    w = torch.where(mask, safe.norm(dim=-1), torch.zeros_like(vec[:, 0]))
+    return w, vec
+
+
+def cosine_cutoff(d: Tensor, rc: float) -> Tensor:
+    """CosineCutoff.forward (layers.py:149-152)."""
+    return 0.5 * (torch.cos(d * math.pi / rc) + 1.0) * (d < rc).to(d.dtype)
+
+
+def expnorm_rbf(d: Tensor, means: Tensor, betas: Tensor, rc: float) -> Tensor:
+    """ExpNormalSmearing.forward (layers.py:744-746), alpha = 5/rc (:725)."""
+    d = d.unsqueeze(-1)
+    alpha = 5.0 / rc
+    return cosine_cutoff(d, rc) * torch.exp(-betas * (torch.exp(alpha * (-d)) - means) ** 2)
+
+
+def sph_harm(lmax: int, u: Tensor) -> Tensor:
+    """TensorInit._calculate_components (layers.py:805-869), degrees 1..lmax, no l=0."""
+    x, y, z = u[..., 0], u[..., 1], u[..., 2]
+    out = [x, y, z]
+    if lmax >= 2:
+        s3 = math.sqrt(3.0)
+        y2 = y * y
+        x2z2 = x * x + z * z
+        s20, s21, s22, s23, s24 = s3 * x * z, s3 * x * y, y2 - 0.5 * x2z2, s3 * y * z, s3 / 2.0 * (z * z - x * x)
+        out += [s20, s21, s22, s23, s24]
+    if lmax >= 3:
+        c42, c7, c168 = math.sqrt(42.0) / 6.0, math.sqrt(7.0), math.sqrt(168.0) / 8.0
+        out += [
+            c42 * (s20 * z + s24 * x),
+            c7 * s20 * y,
+            c168 * (4.0 * y2 - x2z2) * x,
+            0.5 * c7 * y * (2.0 * y2 - 3.0 * x2z2),
+            c168 * z * (4.0 * y2 - x2z2),
+            c7 * s24 * y,
+            c42 * (s24 * z - s20 * x),
+        ]
+    if lmax >= 4:
+        raise NotImplementedError("oracle restates degrees 1..3 (layers.py:822-869)")
+    return torch.stack(out, dim=-1)
+
+
+# --------------------------------------------------------------------------
+# layers
+# --------------------------------------------------------------------------
+def _lin(sd, key, x, bias=True):
+    return F.linear(x, sd[key + ".weight"], sd[key + ".bias"] if bias else None)
+
+
+def node_init(sd, cfg: OracleConfig, z, h0, edge_index, r, phi) -> Tensor:
+    """NodeInit.forward/message (layers.py:1658-1675): self loops dropped, cosine
+    cutoff applied on top of phi (which already holds one), sum at targets, then
+    Dense(2C->C)+LayerNorm+SiLU, Dense(C->C) (:1646-1649, Dense order :523-528)."""
+    src, tgt = edge_index[0], edge_index[1]
+    m = src != tgt
+    src, tgt, r, phi = src[m], tgt[m], r[m], phi[m]
+    feat = _lin(sd, "node_init.W_ndp.dense_layers.0", phi) * cosine_cutoff(r, cfg.cutoff).unsqueeze(-1)
+    msg = sd["node_init.A_nbr.weight"][z][src] * feat
+    agg = torch.zeros_like(h0).index_add_(0, tgt, msg)
+    y = _lin(sd, "node_init.W_nrd_nru.dense_layers.0", torch.cat([h0, agg], dim=1))
+    y = F.layer_norm(y, (cfg.n_atom_basis,), sd["node_init.W_nrd_nru.dense_layers.0.norm.weight"],
+                     sd["node_init.W_nrd_nru.dense_layers.0.norm.bias"], 1e-5)
+    return _lin(sd, "node_init.W_nrd_nru.dense_layers.1", F.silu(y))
+
+
+def edge_init(sd, edge_index, phi, h) -> Tensor:
+    """EdgeInit.message (layers.py:1704-1714): t_ij = (h_i + h_j) * W_erp(phi), loops kept."""
+    return (h[edge_index[1]] + h[edge_index[0]]) * _lin(sd, "edge_init.W_erp", phi)
+
+
+def segment_softmax(a: Tensor, index: Tensor, n: int) -> Tensor:
+    """torch_geometric.utils.softmax (call at gotennet.py:503): detached max shift,
+    denominator + 1e-16."""
+    idx = index.view(-1, *([1] * (a.dim() - 1))).expand_as(a)
+    mx = a.new_full((n,) + a.shape[1:], float("-inf")).scatter_reduce_(0, idx, a.detach(), "amax")
+    e = (a - mx[index]).exp()
+    den = a.new_zeros((n,) + a.shape[1:]).index_add_(0, index, e) + 1e-16
+    return e / den[index]
+
+
+def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges):
+    """GATA.forward / message / aggregate / edge_update (gotennet.py:366-640).
+    h [N,C], X [N,L,C], Y=rl_ij [E,L], t [E,C], r [E], n_edges [E]."""
+    p = f"gata_list.{i}."
+    C, H, S, lmax = cfg.n_atom_basis, cfg.num_heads, cfg.S, cfg.lmax
+    last = i == cfg.n_interactions - 1
+    src, tgt = edge_index[0], edge_index[1]
+    N, E = h.size(0), t.size(0)
+
+    q = _lin(sd, p + "W_q", h).view(N, H, C // H)                     # :400
+    k = _lin(sd, p + "W_k", h).view(N, H, C // H)                     # :401
+    x = _lin(sd, p + "gamma_s.1", F.silu(_lin(sd, p + "gamma_s.0", h)))  # :404
+    v = _lin(sd, p + "gamma_v.1", F.silu(_lin(sd, p + "gamma_v.0", h)))  # :405
+    ta = F.silu(_lin(sd, p + "W_re", t)).view(E, H, C // H)           # :406, :497
+    tf = _lin(sd, p + "W_rs", t)                                      # :407
+
+    a = (q[tgt] * k[src] * ta).sum(-1)                                # :502  [E,H]
+    alpha = segment_softmax(a, tgt, N)                                # :503
+    if cfg.scale_edge:                                                # :506-511
+        alpha = alpha * (torch.sqrt(n_edges).view(-1, 1) / math.sqrt(C))
+    else:
+        alpha = alpha * (1.0 / math.sqrt(C))
+    sea = (alpha.unsqueeze(-1) * v[src].view(E, H, S * C // H)).reshape(E, S * C)  # :516-519
+    spatial = tf * x[src] * cosine_cutoff(r, cfg.cutoff).unsqueeze(-1)  # :522-526
+    o = (spatial + sea).view(E, S, C)                                 # :529-532
+
+    blocks = degree_slices(lmax)
+    kd = [1 + l for l in range(lmax)] if cfg.sep_dir else [1] * lmax  # :538-545
+    nd = lmax if cfg.sep_dir else 1
+    kt = [1 + nd + l for l in range(lmax)] if cfg.sep_tensor else [1 + nd] * lmax  # :548-555
+    Xs = X[src]
+    dX = torch.cat([Y[:, a0:a1, None] * o[:, kd[l], None, :] + Xs[:, a0:a1, :] * o[:, kt[l], None, :]
+                    for l, (a0, a1) in enumerate(blocks)], dim=1)      # :558
+    h = h + torch.zeros_like(h).index_add_(0, tgt, o[:, 0, :])         # :638, :426
+    X = X + torch.zeros_like(X).index_add_(0, tgt, dX)                 # :639, :427
+
+    if not last and cfg.edge_updates:                                  # :429-447
+        EQ = F.linear(X, sd[p + "W_vq.weight"])
+        if cfg.sep_htr:
+            EK = torch.cat([F.linear(X[:, a0:a1], sd[p + f"W_vk.{l}.weight"])
+                            for l, (a0, a1) in enumerate(blocks)], dim=1)
+            groups = blocks
+        else:
+            EK = F.linear(X, sd[p + "W_vk.weight"])
+            groups = [(0, cfg.L)]
+        EQi, EKj = EQ[tgt], EK[src]                                    # _i = target, _j = source
+        w = 0
+        for a0, a1 in groups:                                          # :580-609 (rejection on, :351-364)
+            y = Y[:, a0:a1, None]
+            Qr = EQi[:, a0:a1] - (EQi[:, a0:a1] * y).sum(1, keepdim=True) * y
+            Kr = EKj[:, a0:a1] - (EKj[:, a0:a1] * y).sum(1, keepdim=True) * y
+            w = w + (Qr * Kr).sum(1)
+        t = t + F.silu(_lin(sd, p + "gamma_t.dense_layers.0", t)) * w  # :611, :445
+    return h, X, t
+
+
+def eqff_layer(sd, cfg: OracleConfig, i: int, h, X):
+    """EQFF.forward (gotennet.py:728-748)."""
+    p = f"eqff_list.{i}."
+    C = cfg.n_atom_basis
+    P = F.linear(X, sd[p + "W_vu.weight"])
+    n = torch.sqrt((P * P).sum(dim=-2) + cfg.epsilon)
+    m = _lin(sd, p + "gamma_m.1", F.silu(_lin(sd, p + "gamma_m.0", torch.cat([h, n], dim=-1))))
+    return h + m[:, :C], X + m[:, None, C:] * P
+
+
+def gotennet_forward(sd, cfg: OracleConfig, z, edge_index, edge_diff, edge_vec,
+                     intermediates: Optional[dict] = None):
+    """GotenNet.forward (gotennet.py:956-1010).  Unlike the reference, `edge_vec`
+    is NOT mutated in place (quirk App. C.3)."""
+    src, tgt = edge_index[0], edge_index[1]
+    h = sd["A_na.weight"][z]                                           # :973
+    phi = expnorm_rbf(edge_diff, sd["radial_basis.means"], sd["radial_basis.betas"], cfg.cutoff)  # :974
+    h = node_init(sd, cfg, z, h, edge_index, edge_diff, phi)           # :976
+    t = edge_init(sd, edge_index, phi, h)                              # :977
+    mask = (src != tgt).unsqueeze(-1)                                  # :978-980
+    safe = torch.where(mask, edge_vec, torch.ones_like(edge_vec))
+    u = torch.where(mask, edge_vec / safe.norm(dim=1, keepdim=True), edge_vec)
+    Y = sph_harm(cfg.lmax, u)                                          # :982
+    deg = torch.zeros(h.size(0), dtype=h.dtype).index_add_(0, src, torch.ones_like(edge_diff))  # :986-988
+    n_edges = deg[src]                                                 # :989
+    X = h.new_zeros(h.size(0), cfg.L, cfg.n_atom_basis)                # :992
+    if intermediates is not None:
+        intermediates.update(phi=phi, h0=h, t0=t, Y=Y, n_edges=n_edges)
+    for i in range(cfg.n_interactions):                                # :995-1007
+        h, X, t = gata_layer(sd, cfg, i, edge_index, h, X, Y, t, edge_diff, n_edges)
+        h, X = eqff_layer(sd, cfg, i, h, X)
+        if intermediates is not None:
+            intermediates[f"h{i + 1}"], intermediates[f"X{i + 1}"], intermediates[f"t{i + 1}"] = h, X, t
+    return h, X
+
+
+def wrapper_forward(sd, cfg: OracleConfig, z, pos, batch, intermediates: Optional[dict] = None):
+    """GotenNetWrapper.forward (gotennet.py:1043-1045)."""
+    ei = radius_graph(pos.detach(), batch, cfg.cutoff, cfg.max_num_neighbors, loop=True)
+    w, vec = edge_geometry(pos, ei)
+    if intermediates is not None:
+        intermediates.update(edge_index=ei, edge_weight=w, edge_vec=vec)
+    return gotennet_forward(sd, cfg, z, ei, w, vec, intermediates)
+
+
+# --------------------------------------------------------------------------
+# synthetic molecules (SURVEY.md §8d generator)
+# --------------------------------------------------------------------------
+def synth_batch(kind: str, n_mol: int, seed: int = 0):
+    """Deterministic synthetic batches: returns z [N] int64, pos [N,3] f32, batch [N] int64."""
+    g = torch.Generator().manual_seed(seed)
+    if kind == "qm9":
+        n = (18.0 + 2.94 * torch.randn(n_mol, generator=g)).round().clamp(3, 29).long()
+        sigma0 = 1.45
+    elif kind == "aspirin":
+        n = torch.full((n_mol,), 21, dtype=torch.long)
+        sigma0 = 1.6
+    elif kind == "md22":
+        n = torch.full((n_mol,), 370, dtype=torch.long)
+        sigma0 = 1.5
+    else:
+        raise ValueError(kind)
+    N = int(n.sum())
+    batch = torch.repeat_interleave(torch.arange(n_mol), n)
+    sigma = sigma0 * (n.double() / 18.0).pow(1.0 / 3.0).float()
+    pos = torch.randn(N, 3, generator=g) * sigma[batch].unsqueeze(-1)
+    species = torch.tensor([1, 6, 7, 8, 9])
+    probs = torch.tensor([0.51, 0.35, 0.06, 0.078, 0.002])
+    z = species[torch.multinomial(probs, N, replacement=True, generator=g)]
+    return z, pos, batch

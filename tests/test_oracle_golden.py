@@ -1,0 +1,93 @@
+"""CPU: the oracle restatement reproduces the golden vectors that were produced by
+the verbatim reference (tests/golden/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gotennet_oracle as orc
+from oracle.golden_cases import CASES, blob, grad_fingerprint
+
+TOL = 1e-4  # north_star: within 1e-4 relative, fp32
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a, dtype=torch.float64), torch.as_tensor(b, dtype=torch.float64)
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_oracle_matches_reference_golden(name, golden_dir):
+    spec = CASES[name]
+    cfg = spec["cfg"]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    assert np.array_equal(z.numpy(), gold["z"]) and np.array_equal(pos.numpy(), gold["pos"])
+    sd = orc.make_state_dict(cfg, seed=spec["seed"])
+    sd = {k: v.clone().requires_grad_("radial_basis" not in k) for k, v in sd.items()}
+    pos = pos.clone().requires_grad_(True)
+    inter = {}
+    h, X = orc.wrapper_forward(sd, cfg, z, pos, batch, inter)
+    # integer work: bit exact
+    assert np.array_equal(inter["edge_index"].numpy(), gold["edge_index"])
+    assert rel(inter["edge_weight"].detach(), gold["edge_weight"]) < 1e-6
+    assert rel(h.detach(), gold["h"]) < TOL and rel(X.detach(), gold["X"]) < TOL
+    for i in range(cfg.n_interactions):
+        for s in ("h", "X", "t"):
+            assert rel(inter[f"{s}{i + 1}"].detach(), gold[f"state_{s}{i + 1}"]) < TOL, (s, i)
+    (h.sum() + X.pow(2).sum()).backward()
+    assert rel(pos.grad, gold["grad_pos"]) < TOL
+    n_checked = 0
+    for k in gold.files:
+        if k.startswith("grad_") and k != "grad_pos":
+            g = sd[k[5:]].grad
+            g = torch.zeros_like(sd[k[5:]]) if g is None else g
+            assert rel(grad_fingerprint(g), gold[k]) < TOL, k
+            n_checked += 1
+    assert n_checked == len([s for s in orc.state_dict_spec(cfg)])
+
+
+def test_fp64_tiebreak(golden_dir):
+    """fp32 oracle sits within ~1e-6 of its own fp64 evaluation (noise floor)."""
+    spec = CASES["yaml_l2"]
+    cfg = spec["cfg"]
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    sd = orc.make_state_dict(cfg, seed=spec["seed"])
+    h32, X32 = orc.wrapper_forward(sd, cfg, z, pos, batch)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    h64, X64 = orc.wrapper_forward(sd64, cfg, z, pos.double(), batch)
+    assert rel(h32, h64) < 2e-5 and rel(X32, X64) < 2e-5
+
+
+def test_radius_graph_properties():
+    z, pos, batch = orc.synth_batch("qm9", 16, seed=7)
+    ei = orc.radius_graph(pos, batch, 5.0, 32)
+    src, tgt = ei
+    assert (batch[src] == batch[tgt]).all()
+    # sorted by (target, source), self loops present for every node
+    key = tgt * pos.size(0) + src
+    assert (key[1:] > key[:-1]).all()
+    assert ((src == tgt).sum() == pos.size(0))
+    # truncation keeps the first K sources
+    ei8 = orc.radius_graph(pos, batch, 5.0, 4)
+    deg = torch.bincount(ei8[1], minlength=pos.size(0))
+    assert deg.max() <= 4
+    # empty input
+    assert orc.radius_graph(pos[:0], batch[:0], 5.0).shape == (2, 0)
+
+
+def test_rotation_equivariance_lmax2():
+    """h invariant, l=1 block of X rotates as a vector (valid for lmax<=2)."""
+    spec = CASES["yaml_l2"]
+    cfg = spec["cfg"]
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    sd = {k: v.double() for k, v in orc.make_state_dict(cfg, seed=5).items()}
+    q, _ = torch.linalg.qr(torch.randn(3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0)))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    h1, X1 = orc.wrapper_forward(sd, cfg, z, pos.double(), batch)
+    h2, X2 = orc.wrapper_forward(sd, cfg, z, pos.double() @ q.T, batch)
+    assert rel(h2, h1) < 1e-9
+    assert rel(X2[:, :3], torch.einsum("ab,nbc->nac", q, X1[:, :3])) < 1e-9
+    assert rel(X2[:, 3:].pow(2).sum(1), X1[:, 3:].pow(2).sum(1)) < 1e-9
