@@ -1,0 +1,70 @@
+// Shared device/host helpers for the gotennet_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/gotennet_b200.h"
+
+namespace goten {
+
+extern thread_local char g_err[512];
+int set_error(const char* fmt, ...);
+
+#define GOTEN_CHECK_CUDA(expr)                                                              \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess)                                                                  \
+      return goten::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define GOTEN_CHECK_LAUNCH() GOTEN_CHECK_CUDA(cudaPeekAtLastError())
+
+#define GOTEN_REQUIRE(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return goten::set_error(__VA_ARGS__);             \
+  } while (0)
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- device math
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+// d/dx silu(x) = s + x s (1 - s)
+__device__ __forceinline__ float dsiluf_(float x) {
+  float s = sigmoidf_(x);
+  return s * (1.0f + x * (1.0f - s));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Block-wide sum of one float per thread; result valid in every thread.  `red` needs
+// >= 33 floats of shared memory.  Contains two __syncthreads().
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  t = warp_sum(t);
+  return t;
+}
+
+// degree-l block boundaries inside the L axis: l = 1..lmax occupies [l^2-1, (l+1)^2-1)
+__host__ __device__ __forceinline__ constexpr int blk_lo(int l) { return l * l - 1; }            // l >= 1
+__host__ __device__ __forceinline__ constexpr int blk_hi(int l) { return (l + 1) * (l + 1) - 1; }
+__host__ __device__ __forceinline__ constexpr int deg_of(int m) { return m < 3 ? 1 : (m < 8 ? 2 : (m < 15 ? 3 : 4)); }
+
+}  // namespace goten

@@ -1,0 +1,488 @@
+"""Host-side glue: torch tensors -> raw pointers -> C ABI (include/gotennet_b200.h).
+
+PyTorch is used for device memory, streams and autograd bookkeeping only; every
+arithmetic step of the path runs in the hand-written sm_100a kernels of
+libgotennet_b200.so.  There is no fallback: a missing library or a non-CUDA tensor
+raises.
+
+The three autograd.Functions mirror the reference's blocks
+(reference representation/gotennet.py): `InitBlockFn` = NodeInit + EdgeInit
+(:976-977), `GataBlockFn` = GATA.forward incl. HTR edge update (:366-450),
+`EqffBlockFn` = EQFF.forward (:716-748).  Their backward passes are explicit kernel
+sequences (no autograd graph inside), so saved activations and workspaces are under
+our control.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+
+from ._lib import GotenError, lib
+
+_WS = {}
+_IMPL = {"simt": 1, "tc": 2, "auto": 0}
+
+
+def gemm_impl() -> int:
+    return _IMPL[os.environ.get("GOTEN_GEMM", "auto")]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor], off: int = 0):
+    if t is None:
+        return None
+    return t.data_ptr() + off * t.element_size()
+
+
+def _chk(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise GotenError("gotennet_b200 kernels need CUDA tensors (there is no CPU path)")
+        if not t.is_contiguous():
+            raise GotenError("non-contiguous tensor passed to a kernel")
+
+
+def _f32(t):
+    if t.dtype != torch.float32:
+        raise GotenError(f"float32 expected, got {t.dtype}")
+    return t
+
+
+def workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+# ---------------------------------------------------------------------------
+# thin kernel wrappers
+# ---------------------------------------------------------------------------
+def gemm(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, *, a_off=0, b_off=0, c_off=0, bias=None, add_src=None,
+         ld_add=0, add_off=0, act_out=None, ld_act=0, act_off=0, act_lo=0, act_hi=0, colsum=None, impl=None):
+    """C[M,N] = op(A) op(B) (+bias) (+add_src); see goten_gemm in the header."""
+    L = lib()
+    nbytes = L.cdll.goten_gemm_workspace_bytes(M, N, K, ta, tb)
+    ws = workspace(nbytes, C.device) if nbytes > 0 else None
+    L.call("goten_gemm", _ptr(A, a_off), lda, ta, _ptr(B, b_off), ldb, tb, _ptr(C, c_off), ldc, M, N, K,
+           _ptr(bias), _ptr(add_src, add_off), ld_add, _ptr(act_out, act_off), ld_act, act_lo, act_hi,
+           _ptr(colsum), _ptr(ws), nbytes, gemm_impl() if impl is None else impl, _stream())
+
+
+def linear_fwd(a, w, b=None, *, act=False):
+    """z = a w^T + b ; returns (z, silu(z)) if act else z.   a [M,K], w [N,K]."""
+    _chk(a, w, b)
+    M, K = a.shape
+    N = w.shape[0]
+    z = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    y = torch.empty_like(z) if act else None
+    gemm(a, K, 0, w, K, 1, z, N, M, N, K, bias=b, act_out=y, ld_act=N, act_lo=0, act_hi=N if act else 0)
+    return (z, y) if act else z
+
+
+def linear_bwd(g, a, w, *, need_da=True, need_bias=True, add_src=None):
+    """g [M,N] gradient of z = a w^T + b.  Returns (da [M,K] (+add_src), dw [N,K], db [N])."""
+    _chk(g, a, w)
+    M, N = g.shape
+    K = a.shape[1]
+    da = None
+    if need_da:
+        da = torch.empty(M, K, device=g.device, dtype=torch.float32)
+        gemm(g, N, 0, w, K, 0, da, K, M, K, N, add_src=add_src, ld_add=K)
+    dw = torch.empty(N, K, device=g.device, dtype=torch.float32)
+    db = torch.empty(N, device=g.device, dtype=torch.float32) if need_bias else None
+    gemm(g, N, 1, a, K, 0, dw, K, N, K, M, colsum=db)
+    return da, dw, db
+
+
+def dsilu_mul(g, ldg, g_off, pre, ldp, p_off, out, ldo, o_off, M, N):
+    lib().call("goten_dsilu_mul", _ptr(g, g_off), ldg, _ptr(pre, p_off), ldp, _ptr(out, o_off), ldo, M, N, _stream())
+
+
+def permute_nlc(x, to_degree_major: bool):
+    """[N,L,C] -> [L,N,C] (to_degree_major) or back."""
+    _chk(x)
+    if to_degree_major:
+        n, l, c = x.shape
+        out = torch.empty(l, n, c, device=x.device, dtype=torch.float32)
+    else:
+        l, n, c = x.shape
+        out = torch.empty(n, l, c, device=x.device, dtype=torch.float32)
+    lib().call("goten_permute_nlc", _ptr(x), _ptr(out), n, l, c, 1 if to_degree_major else 0, _stream())
+    return out
+
+
+class PermuteFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, to_dm):
+        ctx.to_dm = to_dm
+        return permute_nlc(x.contiguous(), to_dm)
+
+    @staticmethod
+    def backward(ctx, g):
+        return permute_nlc(g.contiguous(), not ctx.to_dm), None
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """table[idx] (gotennet.py:973 A_na, layers.py:1665 A_nbr) with a deterministic backward."""
+
+    @staticmethod
+    def forward(ctx, table, idx):
+        _chk(table, idx)
+        n, C = idx.numel(), table.shape[1]
+        out = torch.empty(n, C, device=table.device, dtype=torch.float32)
+        lib().call("goten_embedding_fwd", _ptr(table), _ptr(idx), n, C, _ptr(out), _stream())
+        ctx.save_for_backward(idx)
+        ctx.rows = table.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = g.contiguous()
+        n, C = g.shape
+        nparts = max(1, (n + 511) // 512)
+        nbytes = nparts * ctx.rows * C * 4
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
+        out = torch.empty(ctx.rows, C, device=g.device, dtype=torch.float32)
+        lib().call("goten_embedding_bwd", _ptr(g), _ptr(idx), n, C, ctx.rows, _ptr(out), _ptr(ws), nbytes, _stream())
+        return out, None
+
+
+# ---------------------------------------------------------------------------
+# geometry
+# ---------------------------------------------------------------------------
+class EdgeGeometryFn(torch.autograd.Function):
+    """pos (or caller-supplied edge vectors) -> r, Y, fc, phi, u, kappa.
+    components/layers.py:1591-1604, :744-746, :149-152, :805-869; gotennet.py:978-989."""
+
+    @staticmethod
+    def forward(ctx, pos, edge_vec, r_in, means, betas, plan, lmax, cutoff, scale_edge, C):
+        E, L, R = plan.E, (lmax + 1) ** 2 - 1, means.numel()
+        dev = plan.src.device
+        _chk(pos, edge_vec, r_in, means, betas)
+        r = torch.empty(E, device=dev)
+        u = torch.empty(E, 3, device=dev)
+        Y = torch.empty(E, L, device=dev)
+        fc = torch.empty(E, device=dev)
+        kappa = torch.empty(E, device=dev)
+        phi = torch.empty(E, R, device=dev)
+        lib().call("goten_edge_geometry_fwd", _ptr(pos), _ptr(edge_vec), _ptr(r_in), _ptr(plan.src), _ptr(plan.tgt),
+                   _ptr(plan.deg_out), E, lmax, float(cutoff), R, _ptr(means), _ptr(betas), int(scale_edge), C,
+                   _ptr(r), _ptr(u), _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(phi), _stream())
+        ctx.plan, ctx.lmax, ctx.cutoff = plan, lmax, float(cutoff)
+        ctx.from_pos = pos is not None
+        ctx.n_pos = pos.shape[0] if pos is not None else 0
+        ctx.save_for_backward(r, u, means, betas)
+        ctx.mark_non_differentiable(u, kappa)
+        return r, Y, fc, phi, u, kappa
+
+    @staticmethod
+    def backward(ctx, g_r, g_Y, g_fc, g_phi, _gu, _gk):
+        r, u, means, betas = ctx.saved_tensors
+        plan = ctx.plan
+        E = plan.E
+        g_vec = torch.empty(E, 3, device=r.device)
+        g_Y = g_Y.contiguous() if g_Y is not None else None
+        g_fc = g_fc.contiguous() if g_fc is not None else None
+        g_phi = g_phi.contiguous() if g_phi is not None else None
+        lib().call("goten_edge_geometry_bwd", _ptr(r), _ptr(u), _ptr(plan.src), _ptr(plan.tgt), E, ctx.lmax,
+                   ctx.cutoff, means.numel(), _ptr(means), _ptr(betas), _ptr(g_phi), _ptr(g_fc), _ptr(g_Y),
+                   _ptr(g_vec), _stream())
+        if g_r is not None:
+            g_vec = g_vec + g_r.unsqueeze(-1) * u  # d|v|/dv = u (self loops: u = 0)
+        if ctx.from_pos:
+            g_pos = torch.empty(ctx.n_pos, 3, device=r.device)
+            lib().call("goten_edge_vec_to_pos_bwd", _ptr(g_vec), _ptr(plan.tgt_ptr), _ptr(plan.src_ptr),
+                       _ptr(plan.src_perm), ctx.n_pos, _ptr(g_pos), _stream())
+            return g_pos, None, None, None, None, None, None, None, None, None
+        return None, g_vec, None, None, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------
+# init block: NodeInit + EdgeInit  (layers.py:1658-1675, :1704-1714)
+# ---------------------------------------------------------------------------
+class InitBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h0, hnbr, phi, fc, Wphi, bphi, W1, b1, ln_g, ln_b, W2, b2, plan, ln_eps):
+        _chk(h0, hnbr, phi, fc, Wphi, bphi, W1, b1, ln_g, ln_b, W2, b2)
+        L_ = lib()
+        N, C = h0.shape
+        E, R = phi.shape
+        dev = h0.device
+        st = _stream()
+        F = torch.empty(E, 2 * C, device=dev)
+        if E > 0:
+            gemm(phi, R, 0, Wphi, R, 1, F, 2 * C, E, 2 * C, R, bias=bphi)
+        m = torch.empty(N, C, device=dev)
+        L_.call("goten_node_init_agg_fwd", _ptr(F), 2 * C, _ptr(hnbr), _ptr(fc), _ptr(plan.tgt_ptr), _ptr(plan.src),
+                N, C, _ptr(m), st)
+        ctx0 = torch.cat([h0, m], dim=1)
+        y1 = linear_fwd(ctx0, W1, b1)
+        y2 = torch.empty_like(y1)
+        mean = torch.empty(N, device=dev)
+        rstd = torch.empty(N, device=dev)
+        L_.call("goten_ln_silu_fwd", _ptr(y1), _ptr(ln_g), _ptr(ln_b), N, C, float(ln_eps), _ptr(y2), _ptr(mean),
+                _ptr(rstd), st)
+        h = linear_fwd(y2, W2, b2)
+        t = torch.empty(E, C, device=dev)
+        L_.call("goten_edge_init_fwd", _ptr(h), _ptr(F), 2 * C, C, _ptr(plan.src), _ptr(plan.tgt), E, C, _ptr(t), st)
+        ctx.plan = plan
+        ctx.save_for_backward(hnbr, phi, fc, Wphi, W1, ln_g, ln_b, W2, F, ctx0, y1, y2, mean, rstd, h)
+        return h, t
+
+    @staticmethod
+    def backward(ctx, g_h, g_t):
+        hnbr, phi, fc, Wphi, W1, ln_g, ln_b, W2, F, ctx0, y1, y2, mean, rstd, h = ctx.saved_tensors
+        plan = ctx.plan
+        L_ = lib()
+        N, C = h.shape
+        E, R = phi.shape
+        dev = h.device
+        st = _stream()
+        need_geom = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]
+        gF = torch.empty(E, 2 * C, device=dev)
+        g_h = g_h.contiguous() if g_h is not None else torch.zeros(N, C, device=dev)
+        g_t = g_t.contiguous() if g_t is not None else torch.zeros(E, C, device=dev)
+        g_he = torch.empty(N, C, device=dev)
+        L_.call("goten_edge_init_bwd", _ptr(g_t), _ptr(h), _ptr(F), 2 * C, C, _ptr(plan.tgt_ptr), _ptr(plan.src),
+                _ptr(plan.tgt), _ptr(plan.src_ptr), _ptr(plan.src_perm), N, E, C, _ptr(gF), 2 * C, _ptr(g_he), st)
+        g_hh = torch.empty(N, C, device=dev)
+        L_.call("goten_add", _ptr(g_h), _ptr(g_he), _ptr(g_hh), N * C, st)
+        g_y2, dW2, db2 = linear_bwd(g_hh, y2, W2)
+        g_y1 = torch.empty(N, C, device=dev)
+        n_part = 296
+        gpart = torch.empty(2, n_part, C, device=dev)
+        L_.call("goten_ln_silu_bwd", _ptr(g_y2), _ptr(y1), _ptr(ln_g), _ptr(ln_b), _ptr(mean), _ptr(rstd), N, C,
+                _ptr(g_y1), _ptr(gpart, 0), _ptr(gpart, n_part * C), n_part, st)
+        dln = torch.empty(2, C, device=dev)
+        ws = workspace(4 * n_part * C * 4, dev)
+        for k in range(2):
+            L_.call("goten_colsum", _ptr(gpart, k * n_part * C), C, n_part, C, _ptr(dln, k * C), _ptr(ws),
+                    ws.numel(), st)
+        g_ctx0, dW1, db1 = linear_bwd(g_y1, ctx0, W1)
+        g_h0 = g_ctx0[:, :C].contiguous()
+        g_m = g_ctx0[:, C:].contiguous()
+        g_fc = torch.zeros(E, device=dev) if need_geom else None
+        L_.call("goten_node_init_agg_bwd_tgt", _ptr(g_m), _ptr(F), 2 * C, _ptr(hnbr), _ptr(fc), _ptr(plan.tgt_ptr),
+                _ptr(plan.src), N, C, _ptr(gF), 2 * C, _ptr(g_fc), st)
+        g_hnbr = torch.empty(N, C, device=dev)
+        L_.call("goten_node_init_agg_bwd_src", _ptr(g_m), _ptr(F), 2 * C, _ptr(fc), _ptr(plan.src_ptr),
+                _ptr(plan.src_perm), _ptr(plan.tgt), N, C, _ptr(g_hnbr), st)
+        if E > 0:
+            g_phi, dWphi, dbphi = linear_bwd(gF, phi, Wphi, need_da=need_geom)
+        else:
+            g_phi = torch.zeros(E, R, device=dev) if need_geom else None
+            dWphi, dbphi = torch.zeros_like(Wphi), torch.zeros(2 * C, device=dev)
+        return (g_h0, g_hnbr, g_phi, g_fc, dWphi, dbphi, dW1, db1, dln[0], dln[1], dW2, db2, None, None)
+
+
+# ---------------------------------------------------------------------------
+# GATA block: projections + message/softmax/aggregate + HTR edge update
+# ---------------------------------------------------------------------------
+class GataBlockFn(torch.autograd.Function):
+    """Inputs: h [N,C], Xd [L,N,C], t [E,C], geometry (Y [E,L], fc [E], kappa [E]) and the
+    layer parameters in concatenated form:
+      Wn1 [4C,C]/bn1 = [W_q; W_k; gamma_s.0; gamma_v.0]       (gotennet.py:400-405)
+      Ws2 [S*C,C]/bs2 = gamma_s.1,  Wv2/bv2 = gamma_v.1
+      We [(S+1|S+2)C, C]/be = [W_re; W_rs; (gamma_t)]          (:406-407, :611)
+      Wvq [C,C], Wvk [G,C,C] (G = lmax if sep_htr else 1)     (:432-441), absent on the last layer
+    """
+
+    @staticmethod
+    def forward(ctx, h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, plan, cfg):
+        _chk(h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk)
+        L_ = lib()
+        st = _stream()
+        N, C = h.shape
+        L = Xd.shape[0]
+        E = t.shape[0]
+        H, lmax, S = cfg["H"], cfg["lmax"], cfg["S"]
+        htr = Wvq is not None
+        ldz = We.shape[0]
+        dev = h.device
+        SC = S * C
+        # node projections: Z1 = [q | k | pre_s | pre_v], A1 = silu(Z1[:, 2C:])
+        Z1 = torch.empty(N, 4 * C, device=dev)
+        A1 = torch.empty(N, 2 * C, device=dev)
+        gemm(h, C, 0, Wn1, C, 1, Z1, 4 * C, N, 4 * C, C, bias=bn1, act_out=A1, ld_act=2 * C, act_lo=2 * C,
+             act_hi=4 * C)
+        x = torch.empty(N, SC, device=dev)
+        v = torch.empty(N, SC, device=dev)
+        gemm(A1, 2 * C, 0, Ws2, C, 1, x, SC, N, SC, C, bias=bs2)
+        gemm(A1, 2 * C, 0, Wv2, C, 1, v, SC, N, SC, C, bias=bv2, a_off=C)
+        # edge projections (pre-activations; consumers apply SiLU)
+        Ze = torch.empty(E, ldz, device=dev)
+        if E > 0:
+            gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be)
+        h1 = torch.empty_like(h)
+        Xd1 = torch.empty_like(Xd)
+        alpha = torch.empty(E, H, device=dev)
+        L_.call("goten_gata_fwd", _ptr(h), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze), ldz, _ptr(Y),
+                _ptr(fc), _ptr(kappa), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax, cfg["gata_flags"],
+                plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), st)
+        EQ = EK = None
+        t1 = t
+        if htr:
+            EQ = torch.empty_like(Xd1)
+            EK = torch.empty_like(Xd1)
+            gemm(Xd1, C, 0, Wvq, C, 1, EQ, C, L * N, C, C)
+            for g, (lo, hi) in enumerate(cfg["vk_groups"]):
+                rows = (hi - lo) * N
+                gemm(Xd1, C, 0, Wvk, C, 1, EK, C, rows, C, C, a_off=lo * N * C, b_off=g * C * C, c_off=lo * N * C)
+            t1 = torch.empty_like(t)
+            L_.call("goten_htr_fwd", _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, (S + 1) * C, _ptr(t),
+                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(t1), st)
+        ctx.plan, ctx.cfg, ctx.htr = plan, cfg, htr
+        ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK)
+        if htr:
+            return h1, Xd1, t1
+        return h1, Xd1  # last layer: t_ij passes through unchanged (gotennet.py:449-450)
+
+    @staticmethod
+    def backward(ctx, g_h1, g_Xd1, g_t1=None):
+        (h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK) = ctx.saved_tensors
+        plan, cfg, htr = ctx.plan, ctx.cfg, ctx.htr
+        L_ = lib()
+        st = _stream()
+        N, C = h.shape
+        L = Xd.shape[0]
+        E = t.shape[0]
+        H, lmax, S = cfg["H"], cfg["lmax"], cfg["S"]
+        ldz = We.shape[0]
+        SC = S * C
+        dev = h.device
+        need_gY, need_gfc = ctx.needs_input_grad[3], ctx.needs_input_grad[4]
+        g_h1 = g_h1.contiguous() if g_h1 is not None else torch.zeros(N, C, device=dev)
+        g_Xd1 = g_Xd1.contiguous() if g_Xd1 is not None else torch.zeros(L, N, C, device=dev)
+        if g_t1 is not None:
+            g_t1 = g_t1.contiguous()
+        gZe = torch.empty(E, ldz, device=dev)
+        g_Y = torch.zeros(E, L, device=dev) if need_gY else None
+        g_fc = torch.zeros(E, device=dev) if need_gfc else None
+        dWvq = dWvk = None
+        g_Xm = g_Xd1  # gradient reaching the post-message X
+        if htr:
+            if g_t1 is None:
+                g_t1 = torch.zeros(E, C, device=dev)
+            g_EQ = torch.empty_like(Xd1)
+            g_EK = torch.empty_like(Xd1)
+            zt0 = (S + 1) * C
+            L_.call("goten_htr_bwd_tgt", _ptr(g_t1), _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, zt0,
+                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(g_EQ), _ptr(gZe), ldz,
+                    _ptr(g_Y), st)
+            L_.call("goten_htr_bwd_src", _ptr(g_t1), _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, zt0,
+                    _ptr(plan.src_ptr), _ptr(plan.src_perm), _ptr(plan.tgt), N, C, lmax, cfg["htr_flags"],
+                    _ptr(g_EK), st)
+            # X gradient: g_Xm = g_Xd1 + g_EQ Wvq + g_EK^l Wvk_l ; weight gradients
+            g_Xm = torch.empty_like(Xd1)
+            gemm(g_EQ, C, 0, Wvq, C, 0, g_Xm, C, L * N, C, C, add_src=g_Xd1, ld_add=C)
+            dWvq = torch.empty_like(Wvq)
+            gemm(g_EQ, C, 1, Xd1, C, 0, dWvq, C, C, C, L * N)
+            dWvk = torch.empty_like(Wvk)
+            for g, (lo, hi) in enumerate(cfg["vk_groups"]):
+                rows, off = (hi - lo) * N, lo * N * C
+                gemm(g_EK, C, 0, Wvk, C, 0, g_Xm, C, rows, C, C, a_off=off, b_off=g * C * C, c_off=off,
+                     add_src=g_Xm, ld_add=C, add_off=off)
+                gemm(g_EK, C, 1, Xd1, C, 0, dWvk, C, C, C, rows, a_off=off, b_off=off, c_off=g * C * C)
+        # message block
+        g_Z1 = torch.empty(N, 4 * C, device=dev)
+        da = torch.empty(E, H, device=dev)
+        L_.call("goten_gata_bwd_tgt", _ptr(g_h1), _ptr(g_Xm), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze),
+                ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(alpha), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax,
+                cfg["gata_flags"], plan.max_deg_in, _ptr(g_Z1), 4 * C, _ptr(gZe), ldz, _ptr(da), _ptr(g_fc),
+                _ptr(g_Y), st)
+        g_x = torch.empty(N, SC, device=dev)
+        g_v = torch.empty(N, SC, device=dev)
+        g_Xd = torch.empty_like(Xd)
+        L_.call("goten_gata_bwd_src", _ptr(g_h1), _ptr(g_Xm), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze),
+                ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(alpha), _ptr(da), _ptr(plan.src_ptr), _ptr(plan.src_perm),
+                _ptr(plan.tgt), N, C, H, lmax, cfg["gata_flags"], _ptr(g_Z1), 4 * C, _ptr(g_x), _ptr(g_v),
+                _ptr(g_Xd), st)
+        # gamma_s.1 / gamma_v.1
+        g_A1 = torch.empty(N, 2 * C, device=dev)
+        gemm(g_x, SC, 0, Ws2, C, 0, g_A1, 2 * C, N, C, SC)
+        gemm(g_v, SC, 0, Wv2, C, 0, g_A1, 2 * C, N, C, SC, c_off=C)
+        dWs2 = torch.empty_like(Ws2)
+        dbs2 = torch.empty(SC, device=dev)
+        gemm(g_x, SC, 1, A1, 2 * C, 0, dWs2, C, SC, C, N, colsum=dbs2)
+        dWv2 = torch.empty_like(Wv2)
+        dbv2 = torch.empty(SC, device=dev)
+        gemm(g_v, SC, 1, A1, 2 * C, 0, dWv2, C, SC, C, N, b_off=C, colsum=dbv2)
+        # through the SiLU of gamma_s.0 / gamma_v.0 into g_Z1[:, 2C:4C]
+        dsilu_mul(g_A1, 2 * C, 0, Z1, 4 * C, 2 * C, g_Z1, 4 * C, 2 * C, N, 2 * C)
+        g_h = torch.empty_like(h)
+        gemm(g_Z1, 4 * C, 0, Wn1, C, 0, g_h, C, N, C, 4 * C, add_src=g_h1, ld_add=C)
+        dWn1 = torch.empty_like(Wn1)
+        dbn1 = torch.empty(4 * C, device=dev)
+        gemm(g_Z1, 4 * C, 1, h, C, 0, dWn1, C, 4 * C, C, N, colsum=dbn1)
+        # edge projections
+        g_t = torch.empty_like(t)
+        dWe = torch.empty_like(We)
+        dbe = torch.empty(ldz, device=dev)
+        if E > 0:
+            gemm(gZe, ldz, 0, We, C, 0, g_t, C, E, C, ldz, add_src=g_t1, ld_add=C)
+            gemm(gZe, ldz, 1, t, C, 0, dWe, C, ldz, C, E, colsum=dbe)
+        else:
+            dWe.zero_()
+            dbe.zero_()
+        return (g_h, g_Xd, g_t, g_Y, g_fc, None, dWn1, dbn1, dWs2, dbs2, dWv2, dbv2, dWe, dbe, dWvq, dWvk, None, None)
+
+
+# ---------------------------------------------------------------------------
+# EQFF block (gotennet.py:728-748)
+# ---------------------------------------------------------------------------
+class EqffBlockFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, Xd, Wvu, Wm1, bm1, Wm2, bm2, eps):
+        _chk(h, Xd, Wvu, Wm1, bm1, Wm2, bm2)
+        L_ = lib()
+        st = _stream()
+        N, C = h.shape
+        L = Xd.shape[0]
+        dev = h.device
+        P = torch.empty_like(Xd)
+        gemm(Xd, C, 0, Wvu, C, 1, P, C, L * N, C, C)
+        cx = torch.empty(N, 2 * C, device=dev)
+        L_.call("goten_eqff_ctx_fwd", _ptr(h), _ptr(P), N, C, L, float(eps), _ptr(cx), st)
+        Zm, Am = linear_fwd(cx, Wm1, bm1, act=True)
+        M = linear_fwd(Am, Wm2, bm2)
+        h2 = torch.empty_like(h)
+        Xd2 = torch.empty_like(Xd)
+        L_.call("goten_eqff_update_fwd", _ptr(h), _ptr(Xd), _ptr(P), _ptr(M), N, C, L, _ptr(h2), _ptr(Xd2), st)
+        ctx.save_for_backward(Xd, Wvu, Wm1, Wm2, P, cx, Zm, Am, M)
+        return h2, Xd2
+
+    @staticmethod
+    def backward(ctx, g_h2, g_Xd2):
+        Xd, Wvu, Wm1, Wm2, P, cx, Zm, Am, M = ctx.saved_tensors
+        L_ = lib()
+        st = _stream()
+        L, N, C = Xd.shape
+        dev = Xd.device
+        g_h2 = g_h2.contiguous() if g_h2 is not None else torch.zeros(N, C, device=dev)
+        g_Xd2 = g_Xd2.contiguous() if g_Xd2 is not None else torch.zeros(L, N, C, device=dev)
+        g_M = torch.empty(N, 2 * C, device=dev)
+        L_.call("goten_eqff_update_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(P), N, C, L, _ptr(g_M), st)
+        g_Am, dWm2, dbm2 = linear_bwd(g_M, Am, Wm2)
+        g_Zm = torch.empty_like(g_Am)
+        dsilu_mul(g_Am, C, 0, Zm, C, 0, g_Zm, C, 0, N, C)
+        g_cx, dWm1, dbm1 = linear_bwd(g_Zm, cx, Wm1)
+        g_P = torch.empty_like(P)
+        g_h = torch.empty(N, C, device=dev)
+        L_.call("goten_eqff_ctx_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(g_cx), _ptr(P), _ptr(M), _ptr(cx), N, C, L,
+                _ptr(g_P), _ptr(g_h), st)
+        g_Xd = torch.empty_like(Xd)
+        gemm(g_P, C, 0, Wvu, C, 0, g_Xd, C, L * N, C, C, add_src=g_Xd2, ld_add=C)
+        dWvu = torch.empty_like(Wvu)
+        gemm(g_P, C, 1, Xd, C, 0, dWvu, C, C, C, L * N)
+        return g_h, g_Xd, dWvu, dWm1, dbm1, dWm2, dbm2, None

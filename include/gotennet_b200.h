@@ -1,0 +1,241 @@
+/*
+ * gotennet_b200 — C ABI of the B200-native GotenNet interaction path.
+ *
+ * The reference (sarpaykent/GotenNet) is 100 % Python: it has no FFI layer, its
+ * boundary is the nn.Module API (representation/gotennet.py:366, :716, :956, :1026).
+ * This header is therefore the boundary the reference WOULD bind if its hot path
+ * were native: every entry point below names the reference statement(s) it
+ * replaces (file:line relative to /root/reference/gotennet/models/).
+ *
+ * Conventions
+ *   - plain C: raw DEVICE pointers, sizes, leading dimensions, a cudaStream_t
+ *     passed as void*.  No torch types, no C++ exceptions across the ABI.
+ *   - every function returns 0 on success, non-zero on failure;
+ *     goten_last_error() returns a thread-local message.
+ *   - all floating point is IEEE fp32; indices are int32 on the device side
+ *     (edge_index is additionally emitted as int64 for the PyG-style API).
+ *   - edges are stored sorted by (target, source).  `tgt_ptr[N+1]` is the CSR
+ *     over targets; `src_ptr[N+1]` + `src_perm[E]` list edge ids grouped by
+ *     source (ascending target) — the transposed view the backward needs.
+ *   - steerable features are stored DEGREE-MAJOR: Xd[L][N][C] (the reference
+ *     stores [N][L][C]); L = (lmax+1)^2-1.
+ *   - per-layer edge GEMM output Ze[E][ldz]: columns [0,C) = pre-activation of
+ *     W_re, [C,(S+1)C) = W_rs output ("filter"), [(S+1)C,(S+2)C) =
+ *     pre-activation of gamma_t (non-last layers).
+ *   - launches are asynchronous on `stream` unless stated otherwise.
+ */
+#ifndef GOTENNET_B200_H
+#define GOTENNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GOTEN_ABI_VERSION 1
+
+int goten_abi_version(void);
+const char* goten_last_error(void);
+/* device properties the host uses to size launches: out[0]=SM count, out[1]=max smem/block optin, out[2]=cc major*10+minor */
+int goten_device_info(int* out3);
+
+/* ------------------------------------------------------------------ graph --
+ * components/layers.py:1588-1590 (Distance.forward -> torch_cluster.radius_graph,
+ * loop=True, max_num_neighbors=K, CUDA-build semantics: strict d^2 < r^2, same
+ * molecule, first K sources in ascending index, grouped by target).
+ *
+ * Step 1 (count): molecule boundaries from the sorted `batch`, in-degree per
+ * target, exclusive scan -> tgt_ptr.  SYNCHRONISES the stream once to return
+ * E (the host must size the edge arrays) and the number of molecules.
+ *   pos[N][3] f32, batch[N] i64 -> mol_ptr[N+1] i32 (first n_mol+1 entries valid),
+ *   mol_of[N] i32, tgt_ptr[N+1] i32, *n_edges_out, *n_mol_out
+ *   scratch: int32[ 2*N + 4096 ]                                              */
+int goten_radius_graph_count(const float* pos, const int64_t* batch, int n_nodes, float cutoff,
+                             int max_num_neighbors, int loop, int32_t* mol_ptr, int32_t* mol_of,
+                             int32_t* tgt_ptr, int32_t* scratch, int64_t* n_edges_out,
+                             int32_t* n_mol_out, void* stream);
+/* Step 2 (fill): edge lists, int64 edge_index[2][E] (row0 = source, row1 = target),
+ * out-degree per source, src_ptr (scan) and src_perm.  Bit-exact integers.      */
+int goten_radius_graph_fill(const float* pos, const int32_t* mol_ptr, const int32_t* mol_of,
+                            const int32_t* tgt_ptr, int n_nodes, int64_t n_edges, float cutoff,
+                            int max_num_neighbors, int loop, int32_t* src, int32_t* tgt,
+                            int64_t* edge_index, int32_t* deg_out, int32_t* src_ptr,
+                            int32_t* src_perm, int32_t* scratch, void* stream);
+/* Transposed view for an externally supplied, target-sorted edge list
+ * (GotenNet.forward takes edge_index from the caller, gotennet.py:956):
+ * deg_out, src_ptr, src_perm from src/tgt.  `order_by_src[E]` is a stable
+ * argsort of src computed by the caller.                                        */
+int goten_csr_from_sorted(const int32_t* src, const int32_t* tgt, const int32_t* order_by_src,
+                          int n_nodes, int64_t n_edges, int32_t* tgt_ptr, int32_t* deg_out,
+                          int32_t* src_ptr, int32_t* src_perm, int32_t* scratch, void* stream);
+
+/* --------------------------------------------------------------- geometry --
+ * layers.py:1591-1604 (edge_vec, edge_weight), gotennet.py:978-989 (unit vector,
+ * out-degree gather), layers.py:805-869 (TensorInit, degrees 1..lmax<=3),
+ * layers.py:744-746 + :149-152 (ExpNormalSmearing * CosineCutoff).
+ *   -> r[E], u[E][3] (0 on self loops), Y[E][L], fc[E] (cosine cutoff),
+ *      kappa[E] = (scale_edge ? sqrt(deg_out[src]) : 1) / sqrt(C)  (gotennet.py:506-511),
+ *      phi[E][n_rbf]
+ * If `edge_vec_in` != NULL the vectors are taken from it ([E][3], un-normalised,
+ * GotenNet.forward's argument) instead of pos[src]-pos[tgt]; if `r_in` != NULL the
+ * distances fed to the radial basis / cutoff are taken from it (edge_diff).     */
+int goten_edge_geometry_fwd(const float* pos, const float* edge_vec_in, const float* r_in, const int32_t* src,
+                            const int32_t* tgt, const int32_t* deg_out, int64_t n_edges, int lmax,
+                            float cutoff, int n_rbf, const float* means, const float* betas,
+                            int scale_edge, int n_atom_basis, float* r, float* u, float* Y,
+                            float* fc, float* kappa, float* phi, void* stream);
+/* d(loss)/d(edge_vec) from the gradients of phi, fc and Y (first-order forces,
+ * outputs.py:365-375 needs d/dpos).  g_vec[E][3]; the caller scatters it to pos. */
+int goten_edge_geometry_bwd(const float* r, const float* u, const int32_t* src, const int32_t* tgt,
+                            int64_t n_edges, int lmax, float cutoff, int n_rbf, const float* means,
+                            const float* betas, const float* g_phi, const float* g_fc,
+                            const float* g_Y, float* g_vec, void* stream);
+/* scatter of per-edge vector gradients onto positions: g_pos[i] = sum_{e: src=i} g - sum_{e: tgt=i} g */
+int goten_edge_vec_to_pos_bwd(const float* g_vec, const int32_t* tgt_ptr, const int32_t* src_ptr,
+                              const int32_t* src_perm, int n_nodes, float* g_pos, void* stream);
+
+/* ------------------------------------------------------------------- GEMM --
+ * Every nn.Linear / Dense on the path (layers.py:523 -> F.linear), fp32 result
+ * accuracy (the reference runs with TF32 disabled, scripts/train.py:16).
+ *
+ *   C[M][N] = opA(A) * opB(B) (+ bias[N])
+ *   trans_a = 0: A is [M][K] (lda)      trans_a = 1: A is [K][M] (lda)
+ *   trans_b = 0: B is [K][N] (ldb)      trans_b = 1: B is [N][K] (ldb)   (nn.Linear weight)
+ * epilogue:
+ *   act_out != NULL: additionally writes act_out[m][n - act_lo] = silu(C[m][n]) for
+ *     act_lo <= n < act_hi (ld = ld_act); C keeps the pre-activation.
+ *   add_src != NULL: C[m][n] += add_src[m][n] (ld = ld_add; may alias C) — residual /
+ *     gradient-join fused into the GEMM.
+ *   colsum != NULL (trans_a = 1 only): colsum[m] = sum_k A[k][m]  (bias gradient
+ *     fused into the weight-gradient GEMM).
+ * `workspace` (split-K partials): at least goten_gemm_workspace_bytes(...) bytes.
+ * impl: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05 3xTF32.                            */
+int64_t goten_gemm_workspace_bytes(int M, int N, int K, int trans_a, int trans_b);
+int goten_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,
+               float* C, int ldc, int M, int N, int K, const float* bias, const float* add_src,
+               int ld_add, float* act_out, int ld_act, int act_lo, int act_hi, float* colsum,
+               void* workspace, int64_t workspace_bytes, int impl, void* stream);
+/* out[m][n] = g[m][n] * silu'(pre[m][n])  (Dense activation backward, layers.py:527-528) */
+int goten_dsilu_mul(const float* g, int ldg, const float* pre, int ldp, float* out, int ldo,
+                    int64_t M, int N, void* stream);
+/* column sums of a [M][N] matrix (bias gradients of non-fused cases) */
+int goten_colsum(const float* A, int lda, int64_t M, int N, float* out, float* workspace,
+                 int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------- init block --
+ * F[E][2C] = phi * [W_ndp ; W_erp]^T + b is produced by goten_gemm.
+ * NodeInit.message + aggregate (layers.py:1658-1675): self loops skipped,
+ *   m[i][c] = sum_{e->i, j!=i} hnbr[j][c] * F[e][c] * fc[e]                      */
+int goten_node_init_agg_fwd(const float* F, int ldf, const float* hnbr, const float* fc,
+                            const int32_t* tgt_ptr, const int32_t* src, int n_nodes, int C,
+                            float* m, void* stream);
+/* gF[e][c] (cols [0,C) of gF) = g_m[i][c]*hnbr[j][c]*fc[e];  g_fc_acc[e] += sum_c g_m*hnbr*F (optional) */
+int goten_node_init_agg_bwd_tgt(const float* g_m, const float* F, int ldf, const float* hnbr,
+                                const float* fc, const int32_t* tgt_ptr, const int32_t* src,
+                                int n_nodes, int C, float* gF, int ldgf, float* g_fc, void* stream);
+/* g_hnbr[j][c] = sum_{e: src=j, tgt!=j} g_m[i][c]*F[e][c]*fc[e] */
+int goten_node_init_agg_bwd_src(const float* g_m, const float* F, int ldf, const float* fc,
+                                const int32_t* src_ptr, const int32_t* src_perm, const int32_t* tgt,
+                                int n_nodes, int C, float* g_hnbr, void* stream);
+/* Dense(2C->C)+LayerNorm then SiLU (layers.py:523-528 with norm='layer'):
+ * y[n][c] = silu( LN(x[n][:]) * gamma + beta ), eps = 1e-5; saves mean/rstd.     */
+int goten_ln_silu_fwd(const float* x, const float* gamma, const float* beta, int64_t n_rows, int C,
+                      float eps, float* y, float* mean, float* rstd, void* stream);
+int goten_ln_silu_bwd(const float* g_y, const float* x, const float* gamma, const float* beta,
+                      const float* mean, const float* rstd, int64_t n_rows, int C, float* g_x,
+                      float* g_gamma_part, float* g_beta_part, int n_part, void* stream);
+/* EdgeInit.message (layers.py:1711): t[e][c] = (h[i][c] + h[j][c]) * F[e][C + c]  (self loops kept) */
+int goten_edge_init_fwd(const float* h, const float* F, int ldf, int col0, const int32_t* src,
+                        const int32_t* tgt, int64_t n_edges, int C, float* t, void* stream);
+/* gF[e][col0+c] = g_t[e][c]*(h_i+h_j);  g_h[n][c] = sum_{e: tgt=n} g_t*F + sum_{e: src=n} g_t*F */
+int goten_edge_init_bwd(const float* g_t, const float* h, const float* F, int ldf, int col0,
+                        const int32_t* tgt_ptr, const int32_t* src, const int32_t* tgt,
+                        const int32_t* src_ptr, const int32_t* src_perm, int n_nodes, int64_t n_edges,
+                        int C, float* gF, int ldgf, float* g_h, void* stream);
+
+/* ------------------------------------------------------------ GATA block --
+ * GATA.message + softmax + aggregate + residual (gotennet.py:452-559, :503,
+ * :613-640, :426-427), fused; one CTA per target node, neighbours read through
+ * L2, segment softmax and scatter-sum done in-CTA (deterministic, no atomics).
+ *   qk[N][ldqk]: cols [0,C) = q, [C,2C) = k      x[N][S*C], v[N][S*C]
+ *   Xd[L][N][C]   Ze[E][ldz] (see top)           Y[E][L], fc[E], kappa[E]
+ * flags: bit0 = sep_dir, bit1 = sep_tensor.
+ * outputs: h_out[N][C] = h + dh, Xd_out = Xd + dX, alpha[E][H] (normalised
+ * attention weights, saved for the backward).                                  */
+int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, const float* x,
+                   const float* v, const float* Ze, int ldz, const float* Y, const float* fc,
+                   const float* kappa, const int32_t* tgt_ptr, const int32_t* src, int n_nodes,
+                   int C, int H, int lmax, int flags, int max_deg_in, float* h_out, float* Xd_out,
+                   float* alpha, void* stream);
+/* backward, target-centric half: needs g_h[N][C], g_Xd[L][N][C] (gradients of the
+ * block outputs).  Produces g_qk[:, 0:C) (dq), gZe[:, 0:(S+1)C) (d pre-act W_re, d filter),
+ * da[E][H] (gradient of the attention logits) and, if non-NULL, the geometry
+ * gradients g_fc[E] (accumulated) and g_Y[E][L] (accumulated).                 */
+int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, const float* qk,
+                       int ldqk, const float* x, const float* v, const float* Ze, int ldz,
+                       const float* Y, const float* fc, const float* kappa, const float* alpha,
+                       const int32_t* tgt_ptr, const int32_t* src, int n_nodes, int C, int H,
+                       int lmax, int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe,
+                       int ldgz, float* da, float* g_fc, float* g_Y, void* stream);
+/* backward, source-centric half: g_qk[:, C:2C) (dk), g_x, g_v [N][S*C] and
+ * g_Xd_in[L][N][C] = g_Xd + sum over outgoing edges (residual included).      */
+int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, const float* qk,
+                       int ldqk, const float* x, const float* v, const float* Ze, int ldz,
+                       const float* Y, const float* fc, const float* kappa, const float* alpha,
+                       const float* da, const int32_t* src_ptr, const int32_t* src_perm,
+                       const int32_t* tgt, int n_nodes, int C, int H, int lmax, int flags,
+                       float* g_qk, int ldgqk, float* g_x, float* g_v, float* g_Xd_in, void* stream);
+
+/* ------------------------------------------------------------- HTR block --
+ * GATA.edge_update + vector_rejection + residual (gotennet.py:351-364, :561-611,
+ * :445): EQ/EK are [L][N][C] projections of the post-message X;
+ *   w[e][c] = sum_l sum_m rej(EQ_i)^l_m rej(EK_j)^l_m ;  t_out = t + silu(zt) * w
+ * zt = Ze[:, zt_col0 : zt_col0+C).  flags: bit0 = sep_htr (rejection per degree),
+ * bit1 = rejection enabled.                                                    */
+int goten_htr_fwd(const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
+                  int zt_col0, const float* t, const int32_t* tgt_ptr, const int32_t* src,
+                  int n_nodes, int C, int lmax, int flags, float* t_out, void* stream);
+/* target half: g_EQ[L][N][C], gZe[:, zt_col0..) = g_t_out * w * silu'(zt); optional g_Y (accumulated) */
+int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, const float* Y,
+                      const float* Ze, int ldz, int zt_col0, const int32_t* tgt_ptr,
+                      const int32_t* src, int n_nodes, int C, int lmax, int flags, float* g_EQ,
+                      float* gZe, int ldgz, float* g_Y, void* stream);
+/* source half: g_EK[L][N][C] */
+int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, const float* Y,
+                      const float* Ze, int ldz, int zt_col0, const int32_t* src_ptr,
+                      const int32_t* src_perm, const int32_t* tgt, int n_nodes, int C, int lmax,
+                      int flags, float* g_EK, void* stream);
+
+/* ------------------------------------------------------------ EQFF block --
+ * EQFF.forward (gotennet.py:728-748). P = X W_vu^T comes from goten_gemm.
+ * ctx[N][2C] = [ h | sqrt(sum_m P^2 + eps) ]                                   */
+int goten_eqff_ctx_fwd(const float* h, const float* P, int n_nodes, int C, int L, float eps,
+                       float* ctx, void* stream);
+/* h_out = h + m[:, :C];  Xd_out[m][n][c] = Xd + m[n][C+c] * P[m][n][c]  (m = gamma_m output, [N][2C]) */
+int goten_eqff_update_fwd(const float* h, const float* Xd, const float* P, const float* m,
+                          int n_nodes, int C, int L, float* h_out, float* Xd_out, void* stream);
+/* g_m[N][2C] = [ g_h_out | sum_m g_Xd_out * P ] */
+int goten_eqff_update_bwd(const float* g_h_out, const float* g_Xd_out, const float* P, int n_nodes,
+                          int C, int L, float* g_m, void* stream);
+/* g_P = g_Xd_out * m2 + g_ctx[:, C:] * P / n ;  g_h = g_h_out + g_ctx[:, :C]  (n = ctx[:, C:]) */
+int goten_eqff_ctx_bwd(const float* g_h_out, const float* g_Xd_out, const float* g_ctx,
+                       const float* P, const float* m, const float* ctx, int n_nodes, int C, int L,
+                       float* g_P, float* g_h, void* stream);
+
+/* ------------------------------------------------------------ utilities --
+ * out = a + b (gradient joins), layout change [N][L][C] <-> [L][N][C], row gather
+ * (embedding lookup, gotennet.py:973 / layers.py:1665) and its deterministic
+ * scatter-add backward.                                                        */
+int goten_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+int goten_permute_nlc(const float* in, float* out, int n_nodes, int L, int C, int to_degree_major,
+                      void* stream);
+int goten_embedding_fwd(const float* table, const int64_t* idx, int64_t n, int C, float* out,
+                        void* stream);
+int goten_embedding_bwd(const float* g_out, const int64_t* idx, int64_t n, int C, int n_rows,
+                        float* g_table, float* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOTENNET_B200_H */

@@ -1,0 +1,270 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Everything goes through the
+C ABI (ctypes -> libgotennet_b200.so); the oracle is only the checker.
+
+Tolerance: north_star asks for 1e-4 relative in fp32; we use max-abs error divided
+by max-abs of the reference tensor (SURVEY.md §7 'Hard parts').  Integer work
+(edge_index, CSR) must be bit exact."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gotennet_oracle as orc
+from oracle.golden_cases import CASES, blob, grad_fingerprint
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gotennet_b200
+    from gotennet_b200._lib import lib
+    lib()  # fail loudly if the CUDA library is missing
+    return gotennet_b200
+
+
+class Data:
+    pass
+
+
+def build(g, cfg, sd, dev):
+    m = g.GotenNetWrapper(n_atom_basis=cfg.n_atom_basis, n_interactions=cfg.n_interactions, n_rbf=cfg.n_rbf,
+                          cutoff_fn=g.CosineCutoff(cfg.cutoff), max_z=cfg.max_z, epsilon=cfg.epsilon,
+                          num_heads=cfg.num_heads, edge_updates=cfg.edge_updates, scale_edge=cfg.scale_edge,
+                          lmax=cfg.lmax, sep_htr=cfg.sep_htr, sep_dir=cfg.sep_dir, sep_tensor=cfg.sep_tensor,
+                          max_num_neighbors=cfg.max_num_neighbors, activation="swish")
+    m.load_state_dict(orc.expand_aliases(sd), strict=True)
+    return m.to(dev)
+
+
+def make_data(z, pos, batch, dev, grad=True):
+    d = Data()
+    d.z, d.pos, d.batch = z.to(dev), pos.to(dev).requires_grad_(grad), batch.to(dev)
+    return d
+
+
+# ------------------------------------------------------------------ graph -----
+@pytest.mark.parametrize("kind,n_mol,K", [("qm9", 64, 32), ("qm9", 7, 4), ("md22", 2, 32), ("md22", 1, 160)])
+def test_radius_graph_bit_exact(g, dev, kind, n_mol, K):
+    from gotennet_b200.graph import radius_graph_plan
+    z, pos, batch = orc.synth_batch(kind, n_mol, seed=11)
+    ei = orc.radius_graph(pos, batch, 5.0, K)
+    plan = radius_graph_plan(pos.to(dev), batch.to(dev), 5.0, K)
+    assert plan.E == ei.shape[1]
+    assert torch.equal(plan.edge_index.cpu(), ei)
+    src, tgt = plan.src.cpu().long(), plan.tgt.cpu().long()
+    N = pos.shape[0]
+    assert torch.equal(plan.tgt_ptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long),
+                                                             torch.bincount(tgt, minlength=N).cumsum(0)]))
+    assert torch.equal(plan.deg_out.cpu().long()[:N], torch.bincount(src, minlength=N))
+    perm = plan.src_perm.cpu().long()
+    assert torch.equal(perm, torch.sort(src, stable=True).indices)  # grouped by source, ascending target
+
+
+def test_radius_graph_edge_cases(g, dev):
+    from gotennet_b200.graph import radius_graph_plan
+    # single atom, two far-apart atoms, coincident atoms, no-loop variant
+    pos = torch.tensor([[0., 0, 0], [10., 0, 0], [10.5, 0, 0], [3., 3, 3], [3., 3, 3]])
+    batch = torch.tensor([0, 1, 1, 2, 2])
+    for loop in (True, False):
+        ei = orc.radius_graph(pos, batch, 5.0, 32, loop=loop)
+        plan = radius_graph_plan(pos.to(dev), batch.to(dev), 5.0, 32, loop=loop)
+        assert torch.equal(plan.edge_index.cpu(), ei)
+    plan = radius_graph_plan(pos[:0].to(dev), batch[:0].to(dev), 5.0, 32)
+    assert plan.E == 0 and plan.N == 0
+
+
+# ------------------------------------------------------------------- GEMM -----
+@pytest.mark.parametrize("M,N,K", [(1000, 130, 37), (257, 256, 256), (4096, 1792, 256), (33, 5, 3)])
+@pytest.mark.parametrize("impl", [1, 0])
+def test_gemm_layouts(g, dev, M, N, K, impl):
+    from gotennet_b200 import ops
+    gen = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=gen)
+    w = torch.randn(N, K, generator=gen)
+    b = torch.randn(N, generator=gen)
+    add = torch.randn(M, N, generator=gen)
+    ref = a.double() @ w.double().T + b.double() + add.double()
+    A, W, B, ADD = a.to(dev), w.to(dev), b.to(dev), add.to(dev)
+    out = torch.empty(M, N, device=dev)
+    act = torch.empty(M, N, device=dev)
+    ops.gemm(A, K, 0, W, K, 1, out, N, M, N, K, bias=B, add_src=ADD, ld_add=N, act_out=act, ld_act=N, act_lo=0,
+             act_hi=N, impl=impl)
+    assert rel(out, ref) < 2e-6
+    assert rel(act, torch.nn.functional.silu(ref)) < 2e-6
+    # NN: dA = G W
+    gr = torch.randn(M, N, generator=gen)
+    G = gr.to(dev)
+    da = torch.empty(M, K, device=dev)
+    ops.gemm(G, N, 0, W, K, 0, da, K, M, K, N, impl=impl)
+    assert rel(da, gr.double() @ w.double()) < 2e-6
+    # TN: dW = G^T A with fused column sums (split-K path)
+    dw = torch.empty(N, K, device=dev)
+    db = torch.empty(N, device=dev)
+    ops.gemm(G, N, 1, A, K, 0, dw, K, N, K, M, colsum=db, impl=impl)
+    assert rel(dw, gr.double().T @ a.double()) < 2e-6
+    assert rel(db, gr.double().sum(0)) < 2e-6
+    # strided views: column block of a wider matrix
+    wide = torch.randn(M, 3 * K, generator=gen).to(dev)
+    out2 = torch.empty(M, N, device=dev)
+    ops.gemm(wide, 3 * K, 0, W, K, 1, out2, N, M, N, K, a_off=K, impl=impl)
+    assert rel(out2, wide[:, K:2 * K].double().cpu() @ w.double().T) < 2e-6
+
+
+# ------------------------------------------------------- golden vectors -------
+@pytest.mark.parametrize("name", list(CASES))
+def test_golden_forward_backward(g, dev, name, golden_dir):
+    spec = CASES[name]
+    cfg = spec["cfg"]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    m = build(g, cfg, orc.make_state_dict(cfg, seed=spec["seed"]), dev)
+    m._capture = {}
+    d = make_data(z, pos, batch, dev)
+    h, X = m(d)
+    assert np.array_equal(m.last_plan.edge_index.cpu().numpy(), gold["edge_index"])  # bit exact
+    assert rel(h.detach(), gold["h"]) < TOL and rel(X.detach(), gold["X"]) < TOL
+    for i in range(cfg.n_interactions):
+        for s in ("h", "X", "t"):
+            assert rel(m._capture[f"{s}{i + 1}"], gold[f"state_{s}{i + 1}"]) < TOL, (s, i)
+    (h.sum() + X.pow(2).sum()).backward()
+    assert rel(d.pos.grad, gold["grad_pos"]) < TOL
+    params = dict(m.named_parameters())
+    n = 0
+    for k in gold.files:
+        if k.startswith("grad_") and k != "grad_pos":
+            p = params[k[5:]]
+            gr = p.grad if p.grad is not None else torch.zeros_like(p)
+            assert rel(grad_fingerprint(gr.cpu()), gold[k]) < TOL, k
+            n += 1
+    assert n == len(orc.state_dict_spec(cfg))
+
+
+# ------------------------------------- full-width model vs the oracle ----------
+def test_cfg2_width_vs_oracle(g, dev):
+    """BASELINE configs[1] hyper-parameters (C=256, 4 interactions, lmax=2, yaml flags) on 6 QM9-shape
+    molecules: forward and all gradients against the CPU oracle."""
+    cfg = orc.OracleConfig(n_atom_basis=256, n_interactions=4, lmax=2, sep_dir=True, sep_tensor=True,
+                           scale_edge=False)
+    z, pos, batch = orc.synth_batch("qm9", 6, seed=3)
+    sd = orc.make_state_dict(cfg, seed=0)
+    m = build(g, cfg, sd, dev)
+    d = make_data(z, pos, batch, dev)
+    h, X = m(d)
+    (h.sum() + X.pow(2).sum()).backward()
+    sdo = {k: v.clone().requires_grad_("radial_basis" not in k) for k, v in sd.items()}
+    pos_o = pos.clone().requires_grad_(True)
+    ho, Xo = orc.wrapper_forward(sdo, cfg, z, pos_o, batch)
+    (ho.sum() + Xo.pow(2).sum()).backward()
+    assert rel(h.detach(), ho.detach()) < TOL and rel(X.detach(), Xo.detach()) < TOL
+    assert rel(d.pos.grad, pos_o.grad) < TOL
+    params = dict(m.named_parameters())
+    for k, _, _ in orc.state_dict_spec(cfg):
+        gr = params[k].grad
+        go = sdo[k].grad if sdo[k].grad is not None else torch.zeros_like(sdo[k])
+        assert rel(gr, go) < TOL, k
+
+
+def test_rmd17_and_md22_shapes_vs_oracle(g, dev):
+    """configs[2]/[3] flags at reduced size: 6 interactions lmax=2 on aspirin-shape; lmax=3, K=160 on one
+    MD22-shape molecule (long neighbour lists, degree > 32)."""
+    for kind, n_mol, cfg in [
+        ("aspirin", 3, orc.OracleConfig(n_atom_basis=64, n_interactions=6, lmax=2, sep_dir=True, sep_tensor=True,
+                                        scale_edge=False)),
+        ("md22", 1, orc.OracleConfig(n_atom_basis=64, n_interactions=2, lmax=3, sep_dir=True, sep_tensor=True,
+                                     scale_edge=False, max_num_neighbors=160)),
+    ]:
+        z, pos, batch = orc.synth_batch(kind, n_mol, seed=5)
+        sd = orc.make_state_dict(cfg, seed=1)
+        m = build(g, cfg, sd, dev)
+        d = make_data(z, pos, batch, dev)
+        h, X = m(d)
+        (h.sum() + X.pow(2).sum()).backward()
+        pos_o = pos.clone().requires_grad_(True)
+        ho, Xo = orc.wrapper_forward(sd, cfg, z, pos_o, batch)
+        (ho.sum() + Xo.pow(2).sum()).backward()
+        assert rel(h.detach(), ho) < TOL and rel(X.detach(), Xo) < TOL, kind
+        assert rel(d.pos.grad, pos_o.grad) < TOL, kind
+
+
+# ------------------------------------------------- API surface parity ----------
+def test_external_edge_index_and_blocks(g, dev):
+    """GotenNet.forward with a caller-supplied (shuffled) edge list, in-place edge_vec normalisation,
+    and the stand-alone GATA / EQFF module calls."""
+    spec = CASES["yaml_l2"]
+    cfg = spec["cfg"]
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    sd = orc.make_state_dict(cfg, seed=9)
+    m = build(g, cfg, sd, dev)
+    ei = orc.radius_graph(pos, batch, cfg.cutoff, cfg.max_num_neighbors)
+    w, vec = orc.edge_geometry(pos, ei)
+    ho, Xo = orc.gotennet_forward(sd, cfg, z, ei, w, vec)
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))
+    ev = vec[perm].clone().to(dev)
+    h, X = g.GotenNet.forward(m, z.to(dev), ei[:, perm].to(dev), w[perm].to(dev), ev)
+    assert rel(h, ho) < TOL and rel(X, Xo) < TOL
+    nonloop = (ei[0] != ei[1])[perm]
+    assert rel(ev.cpu()[nonloop].norm(dim=1), torch.ones(int(nonloop.sum()))) < 1e-5  # normalised in place
+    # stand-alone blocks
+    N, C, L = z.numel(), cfg.n_atom_basis, cfg.L
+    gen = torch.Generator().manual_seed(1)
+    hh, XX = torch.randn(N, C, generator=gen), torch.randn(N, L, C, generator=gen) * 0.3
+    tt = torch.randn(ei.shape[1], C, generator=gen) * 0.3
+    u = torch.where((ei[0] != ei[1]).unsqueeze(-1), vec / vec.norm(dim=1, keepdim=True).clamp(min=1e-12), vec)
+    Y = orc.sph_harm(cfg.lmax, u)
+    deg = torch.bincount(ei[0], minlength=N).float()[ei[0]]
+    h1, X1, t1 = orc.gata_layer(sd, cfg, 0, ei, hh, XX, Y, tt, w, deg)
+    a, b, c = m.gata_list[0](ei.to(dev), hh.unsqueeze(1).to(dev), XX.to(dev), Y.to(dev), tt.to(dev), w.to(dev),
+                             deg.to(dev))
+    assert a.shape == (N, 1, C) and rel(a.squeeze(1), h1) < TOL and rel(b, X1) < TOL and rel(c, t1) < TOL
+    h2, X2 = orc.eqff_layer(sd, cfg, 0, hh, XX)
+    a, b = m.eqff_list[0](hh.unsqueeze(1).to(dev), XX.to(dev))
+    assert rel(a.squeeze(1), h2) < TOL and rel(b, X2) < TOL
+
+
+# -------------------------------------- size-independent properties ------------
+def test_full_batch_properties(g, dev):
+    """BASELINE configs[1] at full size (B=1024): run-to-run bit stability, rotation invariance of h,
+    rotation equivariance of the l=1 block, permutation of molecules inside the batch."""
+    cfg = orc.OracleConfig(n_atom_basis=256, n_interactions=4, lmax=2, sep_dir=True, sep_tensor=True,
+                           scale_edge=False)
+    z, pos, batch = orc.synth_batch("qm9", 1024, seed=0)
+    m = build(g, cfg, orc.make_state_dict(cfg, seed=0), dev)
+    with torch.no_grad():
+        h1, X1 = m(make_data(z, pos, batch, dev, grad=False))
+        h2, X2 = m(make_data(z, pos, batch, dev, grad=False))
+        assert torch.equal(h1, h2) and torch.equal(X1, X2)  # no atomics anywhere
+        q, _ = torch.linalg.qr(torch.randn(3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0)))
+        if torch.det(q) < 0:
+            q[:, 0] = -q[:, 0]
+        q = q.float()
+        h3, X3 = m(make_data(z, pos @ q.T, batch, dev, grad=False))
+        assert rel(h3, h1) < TOL
+        assert rel(X3[:, :3], torch.einsum("ab,nbc->nac", q.to(dev), X1[:, :3])) < TOL
+        assert rel(X3[:, 3:].pow(2).sum(1), X1[:, 3:].pow(2).sum(1)) < TOL
+        # first 10 molecules alone give the same rows (molecules are independent)
+        n10 = int((batch < 10).sum())
+        h4, X4 = m(make_data(z[:n10], pos[:n10], batch[:n10], dev, grad=False))
+        assert rel(h4, h1[:n10]) < 1e-6 and rel(X4, X1[:n10]) < 1e-6
+
+
+def test_no_cpu_path(g):
+    m = g.GotenNetWrapper(n_atom_basis=32, n_interactions=1, cutoff_fn=g.CosineCutoff(5.0))
+    d = Data()
+    d.z, d.pos, d.batch = torch.ones(3, dtype=torch.long), torch.randn(3, 3), torch.zeros(3, dtype=torch.long)
+    with pytest.raises(g.GotenError):
+        m(d)

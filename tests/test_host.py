@@ -1,0 +1,99 @@
+"""CPU tests of the host side: the C-ABI library loads and exports every symbol the header
+declares (no compute calls), module/state_dict parity with the reference layout, constructor
+error behaviour, and that the product fails loudly without a GPU."""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from oracle import gotennet_oracle as orc
+
+
+@pytest.fixture(scope="module")
+def g():
+    import gotennet_b200
+    return gotennet_b200
+
+
+def test_library_exports_every_declared_symbol():
+    from gotennet_b200 import _build, _lib
+    path = _build.lib_path()
+    if not os.path.exists(path):
+        _build.build()
+    protos = _lib.parse_header()
+    assert len(protos) >= 30
+    cdll = ctypes.CDLL(path)
+    for name in protos:
+        assert hasattr(cdll, name), name
+    assert cdll.goten_abi_version() == 1
+    L = _lib.lib()
+    assert L.cdll.goten_gemm_workspace_bytes(1792, 256, 300000, 1, 0) > 0
+
+
+def test_state_dict_layout_matches_reference_spec(g):
+    cfg = orc.OracleConfig(n_atom_basis=256, n_interactions=4, lmax=2, sep_dir=True, sep_tensor=True, scale_edge=False)
+    m = g.GotenNetWrapper(n_atom_basis=256, n_interactions=4, lmax=2, sep_dir=True, sep_tensor=True, scale_edge=False,
+                          cutoff_fn=g.CosineCutoff(5.0), activation="swish")
+    sd = orc.expand_aliases(orc.make_state_dict(cfg, 0))
+    assert set(sd) == set(m.state_dict())
+    assert len(sd) == 127 and sum(p.numel() for p in m.parameters()) == 7_630_080
+    m.load_state_dict(sd, strict=True)
+    assert m.hidden_dim == 256 and m.cutoff == 5.0 and m.n_interactions == 4 and m.sphere.l == 2
+    # aliased MLP registration
+    a = m.node_init.W_nrd_nru
+    assert a.dense_layers[0].weight is a.layers[0].weight
+
+
+def test_state_dict_matches_reference_module(g):
+    ref_root = "/root/reference"
+    if not os.path.isdir(ref_root):
+        pytest.skip("reference tree not present on this box")
+    from oracle.ref_standins import import_reference
+    ref = import_reference(ref_root)
+    from gotennet.models.components.layers import CosineCutoff
+    for kw in (dict(n_atom_basis=64, n_interactions=2, lmax=1),
+               dict(n_atom_basis=32, n_interactions=3, lmax=3, sep_dir=True, sep_tensor=True, sep_htr=False)):
+        a = ref.GotenNetWrapper(cutoff_fn=CosineCutoff(5.0), **kw).state_dict()
+        b = g.GotenNetWrapper(cutoff_fn=g.CosineCutoff(5.0), **kw).state_dict()
+        assert set(a) == set(b)
+        assert all(a[k].shape == b[k].shape for k in a)
+
+
+def test_constructor_errors(g):
+    with pytest.raises(ValueError):
+        g.GotenNet()  # cutoff_fn is mandatory (the reference dies with AttributeError, gotennet.py:839)
+    with pytest.raises(ValueError):
+        g.GATA(64, torch.nn.functional.silu, edge_updates="bogus")  # gotennet.py:164-167
+    with pytest.raises(NotImplementedError):
+        g.GATA(64, torch.nn.functional.silu, edge_updates="gated")
+    with pytest.raises(NotImplementedError):
+        g.GotenNet(cutoff_fn=g.CosineCutoff(5.0), radial_basis="BesselBasis")
+    with pytest.raises(ValueError):
+        g.GotenNet(cutoff_fn=g.CosineCutoff(5.0), radial_basis="nope")
+    with pytest.raises(ValueError):
+        g.GotenNet(cutoff_fn=g.CosineCutoff(5.0), activation="nope")
+
+
+def test_cpu_tensors_are_rejected(g):
+    m = g.GotenNetWrapper(n_atom_basis=32, n_interactions=1, cutoff_fn=g.CosineCutoff(5.0))
+
+    class D:
+        pass
+
+    d = D()
+    d.z, d.pos, d.batch = torch.ones(3, dtype=torch.long), torch.randn(3, 3), torch.zeros(3, dtype=torch.long)
+    with pytest.raises(g.GotenError):
+        m(d)
+
+
+def test_scalar_utilities_match_oracle(g):
+    d = torch.linspace(0, 6, 50)
+    assert torch.allclose(g.CosineCutoff(5.0)(d), orc.cosine_cutoff(d, 5.0))
+    rb = g.ExpNormalSmearing(cutoff=5.0, n_rbf=32)
+    means, betas = orc.rbf_buffers(orc.OracleConfig())
+    assert torch.equal(rb.means, means) and torch.equal(rb.betas, betas)
+    assert torch.allclose(rb(d), orc.expnorm_rbf(d, means, betas, 5.0))
+    u = torch.nn.functional.normalize(torch.randn(20, 3), dim=1)
+    for l in (1, 2, 3):
+        assert torch.allclose(g.TensorInit(l)(u), orc.sph_harm(l, u))
