@@ -19,7 +19,13 @@ int set_error(const char* fmt, ...);
       return goten::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
   } while (0)
 
-#define GOTEN_CHECK_LAUNCH() GOTEN_CHECK_CUDA(cudaPeekAtLastError())
+// every kernel launch is followed by this macro: it also feeds goten_launch_count()
+extern unsigned long long g_launches;
+#define GOTEN_CHECK_LAUNCH()                    \
+  do {                                          \
+    ++goten::g_launches;                        \
+    GOTEN_CHECK_CUDA(cudaPeekAtLastError());    \
+  } while (0)
 
 #define GOTEN_REQUIRE(cond, ...)                                   \
   do {                                                             \

@@ -17,6 +17,7 @@
 namespace goten {
 
 thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 int set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -402,6 +403,7 @@ extern "C" {
 
 int goten_abi_version(void) { return GOTEN_ABI_VERSION; }
 const char* goten_last_error(void) { return goten::g_err; }
+int64_t goten_launch_count(void) { return (int64_t)goten::g_launches; }
 
 int goten_device_info(int* out3) {
   int dev = 0;

@@ -37,6 +37,8 @@ extern "C" {
 
 int goten_abi_version(void);
 const char* goten_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py's gpu_launches) */
+int64_t goten_launch_count(void);
 /* device properties the host uses to size launches: out[0]=SM count, out[1]=max smem/block optin, out[2]=cc major*10+minor */
 int goten_device_info(int* out3);
 
