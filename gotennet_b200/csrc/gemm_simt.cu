@@ -234,6 +234,17 @@ int gemm_simt(const float* A, int lda, int trans_a, const float* B, int ldb, int
   return 0;
 }
 
+int splitk_finish(const float* partial, const float* partial_cs, int splits, float* C, int ldc, int M, int N,
+                  const float* bias, const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo, int act_hi,
+                  float* colsum, cudaStream_t st) {
+  Epilogue ep{bias, add_src, ld_add, act_out, ld_act, act_lo, act_hi};
+  const size_t total = (size_t)M * N;
+  splitk_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(partial, partial_cs, splits, C, ldc, M, N, ep,
+                                                                        colsum);
+  GOTEN_CHECK_LAUNCH();
+  return 0;
+}
+
 int64_t gemm_simt_workspace_bytes(int M, int N, int K, int trans_a) {
   const int s = pick_splits(M, N, K, trans_a);
   return s > 1 ? (int64_t)s * ((int64_t)M * N + M) * 4 : 0;

@@ -102,27 +102,30 @@ def test_gemm_layouts(g, dev, M, N, K, impl):
     A, W, B, ADD = a.to(dev), w.to(dev), b.to(dev), add.to(dev)
     out = torch.empty(M, N, device=dev)
     act = torch.empty(M, N, device=dev)
+    # impl 1 = exact-fp32 SIMT; impl 0 = auto (tcgen05 3xTF32 where the shape allows): the tensor core
+    # accumulates with truncation, ~2e-8 relative per accumulating MMA (gemm_tc.cu), hence the looser bound
+    tol = 2e-6 if impl == 1 else 2e-5
     ops.gemm(A, K, 0, W, K, 1, out, N, M, N, K, bias=B, add_src=ADD, ld_add=N, act_out=act, ld_act=N, act_lo=0,
              act_hi=N, impl=impl)
-    assert rel(out, ref) < 2e-6
-    assert rel(act, torch.nn.functional.silu(ref)) < 2e-6
+    assert rel(out, ref) < tol
+    assert rel(act, torch.nn.functional.silu(ref)) < tol
     # NN: dA = G W
     gr = torch.randn(M, N, generator=gen)
     G = gr.to(dev)
     da = torch.empty(M, K, device=dev)
     ops.gemm(G, N, 0, W, K, 0, da, K, M, K, N, impl=impl)
-    assert rel(da, gr.double() @ w.double()) < 2e-6
+    assert rel(da, gr.double() @ w.double()) < tol
     # TN: dW = G^T A with fused column sums (split-K path)
     dw = torch.empty(N, K, device=dev)
     db = torch.empty(N, device=dev)
     ops.gemm(G, N, 1, A, K, 0, dw, K, N, K, M, colsum=db, impl=impl)
-    assert rel(dw, gr.double().T @ a.double()) < 2e-6
-    assert rel(db, gr.double().sum(0)) < 2e-6
+    assert rel(dw, gr.double().T @ a.double()) < tol
+    assert rel(db, gr.double().sum(0)) < tol
     # strided views: column block of a wider matrix
     wide = torch.randn(M, 3 * K, generator=gen).to(dev)
     out2 = torch.empty(M, N, device=dev)
     ops.gemm(wide, 3 * K, 0, W, K, 1, out2, N, M, N, K, a_off=K, impl=impl)
-    assert rel(out2, wide[:, K:2 * K].double().cpu() @ w.double().T) < 2e-6
+    assert rel(out2, wide[:, K:2 * K].double().cpu() @ w.double().T) < tol
 
 
 # ------------------------------------------------------- golden vectors -------
