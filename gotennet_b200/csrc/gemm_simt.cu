@@ -311,7 +311,7 @@ __global__ void embedding_fwd_kernel(const float* __restrict__ table, const int6
   out[i] = table[idx[row] * C + c];
 }
 
-constexpr int EMB_ROWS = 512;  // nodes per partial block
+constexpr int EMB_ROWS = 64;  // nodes per partial block
 // part[b][z][c] = sum over nodes of block b with idx == z; one thread per channel -> no conflicts
 __global__ void embedding_bwd_partial_kernel(const float* __restrict__ g, const int64_t* __restrict__ idx, int64_t n,
                                              int C, int n_rows, float* __restrict__ part) {

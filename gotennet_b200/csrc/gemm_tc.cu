@@ -131,6 +131,7 @@ struct Params {
   const float* bias;
   const float* add_src; int ld_add;
   float* act_out; int ld_act, act_lo, act_hi;
+  int add_vec, c_vec;     // 16 B alignment of the add_src / C rows (vector epilogue accesses allowed)
   float* partial;         // split-K partials [splits][M][N] (nullptr: direct epilogue)
   float* colsum;          // column sums of A (MN-major only), direct
   float* partial_colsum;  // [splits][M]
@@ -366,25 +367,49 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           ++n_store;
         } else {
           __syncwarp();
-          const int n = nc0 + lane;
-          const bool ncol = n < p.N;
-          const bool act = p.act_out && ncol && n >= p.act_lo && n < p.act_hi;
+          // 8 lanes x float4 cover the 32 columns of a row; a warp instruction handles 4 rows.  All residual
+          // loads of the chunk are issued before any use (8 independent 128-bit loads per lane).
+          const int cq = lane & 7, rsub = lane >> 3;
+          const int n = nc0 + cq * 4;
+          const bool vec_ok = (n + 3 < p.N);
+          float4 addv[8];
 #pragma unroll
-          for (int r0 = 0; r0 < 32; r0 += 8) {
-            float addv[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int m = row_base + r0 + i;
-              addv[i] = (p.add_src && ncol && m < p.M) ? p.add_src[(size_t)m * p.ld_add + n] : 0.f;
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub, m = row_base + rr;
+            addv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.add_src && m < p.M) {
+              const float* ap = p.add_src + (size_t)m * p.ld_add + n;
+              if (vec_ok && p.add_vec) addv[it] = *reinterpret_cast<const float4*>(ap);
+              else {
+                if (n + 0 < p.N) addv[it].x = ap[0];
+                if (n + 1 < p.N) addv[it].y = ap[1];
+                if (n + 2 < p.N) addv[it].z = ap[2];
+                if (n + 3 < p.N) addv[it].w = ap[3];
+              }
             }
+          }
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int rr = r0 + i, m = row_base + rr;
-              const float v = *reinterpret_cast<const float*>(buf + rr * 128 + (((lane >> 2) ^ (rr & 7)) << 4) +
-                                                              (lane & 3) * 4) + addv[i];
-              if (ncol && m < p.M) {
-                p.C[(size_t)m * p.ldc + n] = v;
-                if (act) p.act_out[(size_t)m * p.ld_act + (n - p.act_lo)] = v / (1.0f + __expf(-v));
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub, m = row_base + rr;
+            float4 v = *reinterpret_cast<const float4*>(buf + rr * 128 + ((cq ^ (rr & 7)) << 4));
+            v.x += addv[it].x; v.y += addv[it].y; v.z += addv[it].z; v.w += addv[it].w;
+            if (m < p.M) {
+              float* cp = p.C + (size_t)m * p.ldc + n;
+              if (vec_ok && p.c_vec) *reinterpret_cast<float4*>(cp) = v;
+              else {
+                if (n + 0 < p.N) cp[0] = v.x;
+                if (n + 1 < p.N) cp[1] = v.y;
+                if (n + 2 < p.N) cp[2] = v.z;
+                if (n + 3 < p.N) cp[3] = v.w;
+              }
+              if (p.act_out) {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  const int nn = n + qd;
+                  if (nn < p.N && nn >= p.act_lo && nn < p.act_hi)
+                    p.act_out[(size_t)m * p.ld_act + (nn - p.act_lo)] = vv[qd] / (1.0f + __expf(-vv[qd]));
+                }
               }
             }
           }
@@ -591,6 +616,8 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
   p.splits = t.splits; p.kb_per_split = t.kb_per_split; p.kb_total = t.kb_total;
   p.C = C; p.ldc = ldc; p.bias = bias; p.add_src = add_src; p.ld_add = ld_add;
   p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
+  p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
+  p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
   p.partial = partial; p.colsum = colsum; p.partial_colsum = partial_cs;
   if (t.splits > 1) { p.bias = nullptr; p.add_src = nullptr; p.act_out = nullptr; }  // applied by splitk_finish
 

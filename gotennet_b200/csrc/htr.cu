@@ -87,29 +87,63 @@ __device__ __forceinline__ void group_grad_y(const float* q, const float* k, con
     gy[m] = dw * (-a * (k[m] - b * y[m]) - b * (q[m] - a * y[m]) - sk * q[m] - sq * k[m]);
 }
 
-template <int LMAX>
+// ---- V-wide channel vectors (V = 4: 128-bit loads/stores; V = 1 fallback)
+template <int V>
+__device__ __forceinline__ void ldv(const float* __restrict__ p, float* out) {
+  if (V == 4) {
+    const float4 t = *reinterpret_cast<const float4*>(p);
+    out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  } else {
+#pragma unroll
+    for (int q = 0; q < V; ++q) out[q] = p[q];
+  }
+}
+template <int V>
+__device__ __forceinline__ void stv(float* __restrict__ p, const float* in) {
+  if (V == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+  } else {
+#pragma unroll
+    for (int q = 0; q < V; ++q) p[q] = in[q];
+  }
+}
+// gather column q of an [L][V] register tile into a contiguous [L] array (compile-time indices)
+template <int L, int V>
+__device__ __forceinline__ void col_of(const float (*a)[V], int q, float* out) {
+#pragma unroll
+  for (int m = 0; m < L; ++m) out[m] = a[m][q];
+}
+
+template <int LMAX, int V>
 __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __restrict__ EK, const float* __restrict__ Y,
                                const float* __restrict__ Ze, int ldz, int zt_col0, const float* __restrict__ t,
                                const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
                                int flags, float* __restrict__ t_out) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
-  const int i = blockIdx.x, c = threadIdx.x;
+  const int i = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
-  float q[L];
+  float q[L][V];
 #pragma unroll
-  for (int m = 0; m < L; ++m) q[m] = EQ[((size_t)m * N + i) * C + c];
+  for (int m = 0; m < L; ++m) ldv<V>(EQ + ((size_t)m * N + i) * C + c, q[m]);
   for (int e = tgt_ptr[i]; e < tgt_ptr[i + 1]; ++e) {
     const int j = src[e];
-    float k[L], y[L];
+    float k[L][V], y[L], zt[V], tv[V];
 #pragma unroll
-    for (int m = 0; m < L; ++m) { k[m] = EK[((size_t)m * N + j) * C + c]; y[m] = Y[(size_t)e * L + m]; }
-    const float w = htr_weight<LMAX>(q, k, y, flags);
-    const float zt = Ze[(size_t)e * ldz + zt_col0 + c];
-    t_out[(size_t)e * C + c] = fmaf(siluf_(zt), w, t[(size_t)e * C + c]);
+    for (int m = 0; m < L; ++m) { ldv<V>(EK + ((size_t)m * N + j) * C + c, k[m]); y[m] = Y[(size_t)e * L + m]; }
+    ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
+    ldv<V>(t + (size_t)e * C + c, tv);
+#pragma unroll
+    for (int qq = 0; qq < V; ++qq) {
+      float qc[L], kc[L];
+      col_of<L, V>(q, qq, qc);
+      col_of<L, V>(k, qq, kc);
+      tv[qq] = fmaf(siluf_(zt[qq]), htr_weight<LMAX>(qc, kc, y, flags), tv[qq]);
+    }
+    stv<V>(t_out + (size_t)e * C + c, tv);
   }
 }
 
-template <int LMAX>
+template <int LMAX, int V>
 __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
                                    const float* __restrict__ EK, const float* __restrict__ Y,
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
@@ -118,37 +152,55 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
                                    float* __restrict__ g_Y) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   __shared__ float red[33];
-  const int i = blockIdx.x, c = threadIdx.x;
+  const int i = blockIdx.x, c = threadIdx.x * V;
   const bool act = c < C;
-  float q[L], gq[L];
+  float q[L][V], gq[L][V];
 #pragma unroll
-  for (int m = 0; m < L; ++m) { q[m] = act ? EQ[((size_t)m * N + i) * C + c] : 0.f; gq[m] = 0.f; }
+  for (int m = 0; m < L; ++m) {
+#pragma unroll
+    for (int qq = 0; qq < V; ++qq) { q[m][qq] = 0.f; gq[m][qq] = 0.f; }
+    if (act) ldv<V>(EQ + ((size_t)m * N + i) * C + c, q[m]);
+  }
   for (int e = tgt_ptr[i]; e < tgt_ptr[i + 1]; ++e) {
     const int j = src[e];
-    float k[L], y[L];
+    float y[L], gy[L];
 #pragma unroll
-    for (int m = 0; m < L; ++m) { k[m] = act ? EK[((size_t)m * N + j) * C + c] : 0.f; y[m] = Y[(size_t)e * L + m]; }
-    float dw = 0.f;
+    for (int m = 0; m < L; ++m) { y[m] = Y[(size_t)e * L + m]; gy[m] = 0.f; }
     if (act) {
-      const float w = htr_weight<LMAX>(q, k, y, flags);
-      const float zt = Ze[(size_t)e * ldz + zt_col0 + c];
-      const float dt = g_t_out[(size_t)e * C + c];
-      gZe[(size_t)e * ldgz + zt_col0 + c] = dt * w * dsiluf_(zt);
-      dw = dt * siluf_(zt);
-      htr_grad<LMAX>(k, y, flags, dw, gq);
-    }
-    if (g_Y != nullptr) {  // block-uniform: geometry gradient for forces
-      float gy[L];
+      float k[L][V], zt[V], dt[V], gz[V];
 #pragma unroll
-      for (int m = 0; m < L; ++m) gy[m] = 0.f;
-      if (flags & HTR_REJ) {
-        if (!(flags & HTR_SEP)) group_grad_y<0, L>(q, k, y, dw, gy);
-        else {
-          group_grad_y<0, 3>(q, k, y, dw, gy);
-          if (LMAX >= 2) group_grad_y<3, 8>(q, k, y, dw, gy);
-          if (LMAX >= 3) group_grad_y<8, 15>(q, k, y, dw, gy);
+      for (int m = 0; m < L; ++m) ldv<V>(EK + ((size_t)m * N + j) * C + c, k[m]);
+      ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
+      ldv<V>(g_t_out + (size_t)e * C + c, dt);
+#pragma unroll
+      for (int qq = 0; qq < V; ++qq) {
+        float qc[L], kc[L], gc[L];
+        col_of<L, V>(q, qq, qc);
+        col_of<L, V>(k, qq, kc);
+        col_of<L, V>(gq, qq, gc);
+        const float w = htr_weight<LMAX>(qc, kc, y, flags);
+        gz[qq] = dt[qq] * w * dsiluf_(zt[qq]);
+        const float dw = dt[qq] * siluf_(zt[qq]);
+        htr_grad<LMAX>(kc, y, flags, dw, gc);
+#pragma unroll
+        for (int m = 0; m < L; ++m) gq[m][qq] = gc[m];
+        if (g_Y != nullptr && (flags & HTR_REJ)) {
+          float g1[L];
+#pragma unroll
+          for (int m = 0; m < L; ++m) g1[m] = 0.f;
+          if (!(flags & HTR_SEP)) group_grad_y<0, L>(qc, kc, y, dw, g1);
+          else {
+            group_grad_y<0, 3>(qc, kc, y, dw, g1);
+            if (LMAX >= 2) group_grad_y<3, 8>(qc, kc, y, dw, g1);
+            if (LMAX >= 3) group_grad_y<8, 15>(qc, kc, y, dw, g1);
+          }
+#pragma unroll
+          for (int m = 0; m < L; ++m) gy[m] += g1[m];
         }
       }
+      stv<V>(gZe + (size_t)e * ldgz + zt_col0 + c, gz);
+    }
+    if (g_Y != nullptr) {  // block-uniform: geometry gradient for forces
 #pragma unroll
       for (int m = 0; m < L; ++m) {
         const float s = block_sum(gy[m], red);
@@ -158,11 +210,11 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
   }
   if (act) {
 #pragma unroll
-    for (int m = 0; m < L; ++m) g_EQ[((size_t)m * N + i) * C + c] = gq[m];
+    for (int m = 0; m < L; ++m) stv<V>(g_EQ + ((size_t)m * N + i) * C + c, gq[m]);
   }
 }
 
-template <int LMAX>
+template <int LMAX, int V>
 __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
                                    const float* __restrict__ EK, const float* __restrict__ Y,
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
@@ -170,42 +222,59 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
                                    const int32_t* __restrict__ tgt, int N, int C, int flags,
                                    float* __restrict__ g_EK) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
-  const int j = blockIdx.x, c = threadIdx.x;
+  const int j = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
-  float k[L], gk[L];
+  float gk[L][V];
 #pragma unroll
-  for (int m = 0; m < L; ++m) { k[m] = EK[((size_t)m * N + j) * C + c]; gk[m] = 0.f; }
-  (void)k;
+  for (int m = 0; m < L; ++m)
+#pragma unroll
+    for (int qq = 0; qq < V; ++qq) gk[m][qq] = 0.f;
   for (int p = src_ptr[j]; p < src_ptr[j + 1]; ++p) {
     const int e = src_perm[p];
     const int i = tgt[e];
-    float q[L], y[L];
+    float q[L][V], y[L], zt[V], dt[V];
 #pragma unroll
-    for (int m = 0; m < L; ++m) { q[m] = EQ[((size_t)m * N + i) * C + c]; y[m] = Y[(size_t)e * L + m]; }
-    const float zt = Ze[(size_t)e * ldz + zt_col0 + c];
-    const float dw = g_t_out[(size_t)e * C + c] * siluf_(zt);
-    htr_grad<LMAX>(q, y, flags, dw, gk);  // d w / d k = P (q - a y) dw : same form with q <-> k
+    for (int m = 0; m < L; ++m) { ldv<V>(EQ + ((size_t)m * N + i) * C + c, q[m]); y[m] = Y[(size_t)e * L + m]; }
+    ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
+    ldv<V>(g_t_out + (size_t)e * C + c, dt);
+#pragma unroll
+    for (int qq = 0; qq < V; ++qq) {
+      float qc[L], gc[L];
+      col_of<L, V>(q, qq, qc);
+      col_of<L, V>(gk, qq, gc);
+      htr_grad<LMAX>(qc, y, flags, dt[qq] * siluf_(zt[qq]), gc);  // d w / d k = P (q - a y) dw : q <-> k symmetric
+#pragma unroll
+      for (int m = 0; m < L; ++m) gk[m][qq] = gc[m];
+    }
   }
 #pragma unroll
-  for (int m = 0; m < L; ++m) g_EK[((size_t)m * N + j) * C + c] = gk[m];
+  for (int m = 0; m < L; ++m) stv<V>(g_EK + ((size_t)m * N + j) * C + c, gk[m]);
 }
 
-static inline int block_for(int C) { return ((C + 31) / 32) * 32; }
+static inline int block_for(int C, int V) { return (((C + V - 1) / V + 31) / 32) * 32; }
 
 }  // namespace goten
 
 using namespace goten;
 
-#define HTR_DISPATCH(KERNEL, ...)                                                              \
+#define HTR_DISPATCH(KERNEL, V4OK, ...)                                                        \
   do {                                                                                         \
     GOTEN_REQUIRE(lmax >= 1 && lmax <= 3, "lmax=%d unsupported (1..3)", lmax);                 \
-    GOTEN_REQUIRE(C >= 1 && C <= 1024, "n_atom_basis=%d unsupported (<=1024)", C);             \
+    GOTEN_REQUIRE(C >= 1 && C <= 4096, "n_atom_basis=%d unsupported (<=4096)", C);             \
     if (N == 0) return 0;                                                                      \
-    const int T = block_for(C);                                                                \
     cudaStream_t st = as_stream(stream);                                                       \
-    if (lmax == 1) KERNEL<1><<<N, T, 0, st>>>(__VA_ARGS__);                                    \
-    else if (lmax == 2) KERNEL<2><<<N, T, 0, st>>>(__VA_ARGS__);                               \
-    else KERNEL<3><<<N, T, 0, st>>>(__VA_ARGS__);                                              \
+    if (V4OK) {                                                                                \
+      const int T = block_for(C, 4);                                                           \
+      if (lmax == 1) KERNEL<1, 4><<<N, T, 0, st>>>(__VA_ARGS__);                               \
+      else if (lmax == 2) KERNEL<2, 4><<<N, T, 0, st>>>(__VA_ARGS__);                          \
+      else KERNEL<3, 4><<<N, T, 0, st>>>(__VA_ARGS__);                                         \
+    } else {                                                                                   \
+      const int T = block_for(C, 1);                                                           \
+      GOTEN_REQUIRE(T <= 1024, "n_atom_basis=%d needs 16-byte aligned rows", C);               \
+      if (lmax == 1) KERNEL<1, 1><<<N, T, 0, st>>>(__VA_ARGS__);                               \
+      else if (lmax == 2) KERNEL<2, 1><<<N, T, 0, st>>>(__VA_ARGS__);                          \
+      else KERNEL<3, 1><<<N, T, 0, st>>>(__VA_ARGS__);                                         \
+    }                                                                                          \
     GOTEN_CHECK_LAUNCH();                                                                      \
     return 0;                                                                                  \
   } while (0)
@@ -215,20 +284,20 @@ extern "C" {
 int goten_htr_fwd(const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz, int zt_col0,
                   const float* t, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
                   float* t_out, void* stream) {
-  HTR_DISPATCH(htr_fwd_kernel, EQ, EK, Y, Ze, ldz, zt_col0, t, tgt_ptr, src, N, C, flags, t_out);
+  HTR_DISPATCH(htr_fwd_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), EQ, EK, Y, Ze, ldz, zt_col0, t, tgt_ptr, src, N, C, flags, t_out);
 }
 
 int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
                       float* g_EQ, float* gZe, int ldgz, float* g_Y, void* stream) {
-  HTR_DISPATCH(htr_bwd_tgt_kernel, g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
+  HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
                g_Y);
 }
 
 int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* src_ptr, const int32_t* src_perm, const int32_t* tgt, int N, int C,
                       int lmax, int flags, float* g_EK, void* stream) {
-  HTR_DISPATCH(htr_bwd_src_kernel, g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, src_ptr, src_perm, tgt, N, C, flags, g_EK);
+  HTR_DISPATCH(htr_bwd_src_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, src_ptr, src_perm, tgt, N, C, flags, g_EK);
 }
 
 }  // extern "C"

@@ -150,7 +150,7 @@ class EmbeddingFn(torch.autograd.Function):
         (idx,) = ctx.saved_tensors
         g = g.contiguous()
         n, C = g.shape
-        nparts = max(1, (n + 511) // 512)
+        nparts = max(1, (n + 63) // 64)
         nbytes = nparts * ctx.rows * C * 4
         ws = torch.empty(nbytes, dtype=torch.uint8, device=g.device)
         out = torch.empty(ctx.rows, C, device=g.device, dtype=torch.float32)
