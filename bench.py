@@ -109,8 +109,9 @@ def run_ours(args):
     torch.manual_seed(0)
     model = g.GotenNetWrapper(cutoff_fn=g.CosineCutoff(CUTOFF), max_num_neighbors=MAX_NBR, activation="swish",
                               **MODEL).to(dev)
+    from gotennet_b200.parallel import FlatGradBuffer
     params = [p for p in model.parameters()]
-    flat = torch.zeros(sum(p.numel() for p in params), device=dev)
+    fbuf = FlatGradBuffer(params)  # one flat fp32 buffer -> one NCCL all-reduce per step
 
     B = args.batch
     z, pos, batch = synth_batch("qm9", B, seed=1000 + rank)  # molecules shard by graph: each rank owns B
@@ -148,8 +149,7 @@ def run_ours(args):
         loss = h.sum() + X.pow(2).sum()
         loss.backward()
         if world > 1:
-            torch._foreach_copy_(list(flat.split([p.numel() for p in params])), [p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
+            fbuf.all_reduce()
         if host_inputs:
             return float(loss.item())  # D2H read of the step's result
         return loss

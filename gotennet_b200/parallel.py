@@ -1,0 +1,73 @@
+"""Data parallelism for the GotenNet path: molecules shard by graph, gradients meet in ONE collective.
+
+`radius_graph` never links atoms of different molecules (reference components/layers.py:1589), so
+the forward/backward of a shard needs no halo and no exchange.  The only cross-GPU step is the
+gradient reduction that Lightning DDP performs implicitly in the reference
+(configs/trainer/default.yaml:7): here it is a single all-reduce over a flat fp32 buffer (7.63 M
+parameters = 30.5 MB for the cfg2 model), NCCL over NVLink/NVSwitch on GPUs, gloo in the CPU tests.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(weights: Sequence[float], world: int) -> List[Tuple[int, int]]:
+    """Contiguous chunks [lo, hi) of molecules per rank, balanced by `weights` (e.g. edges per
+    molecule ~ n_atoms^2).  Every molecule lands on exactly one rank; empty shards are allowed."""
+    w = torch.as_tensor(list(weights), dtype=torch.float64)
+    n = w.numel()
+    if world <= 1:
+        return [(0, n)]
+    cum = torch.cumsum(w, 0)
+    total = float(cum[-1]) if n > 0 else 0.0
+    cuts = [0]
+    for r in range(1, world):
+        target = total * r / world
+        idx = int(torch.searchsorted(cum, torch.tensor(target, dtype=torch.float64)).item())
+        cuts.append(max(cuts[-1], min(idx, n)))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def take_shard(z: torch.Tensor, pos: torch.Tensor, batch: torch.Tensor, lo: int, hi: int):
+    """Atoms of molecules [lo, hi) with batch ids renumbered from 0 (batch must be sorted)."""
+    sel = (batch >= lo) & (batch < hi)
+    return z[sel], pos[sel], batch[sel] - lo
+
+
+class FlatGradBuffer:
+    """Flat fp32 gradient buffer: pack -> one all-reduce -> unpack (views, no extra copy)."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        self.sizes = [p.numel() for p in self.params]
+        dev = self.params[0].device if self.params else torch.device("cpu")
+        self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=dev)
+        self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+
+    def pack(self) -> torch.Tensor:
+        srcs, dsts = [], []
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                srcs.append(p.grad)
+                dsts.append(v)
+        if dsts:
+            torch._foreach_copy_(dsts, srcs)
+        return self.flat
+
+    def all_reduce(self, group: Optional[dist.ProcessGroup] = None, average: bool = False) -> torch.Tensor:
+        self.pack()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.flat, group=group)
+            if average:
+                self.flat.div_(dist.get_world_size(group))
+        return self.flat
+
+    def unpack(self) -> None:
+        for p, v in zip(self.params, self.views):
+            p.grad = v
