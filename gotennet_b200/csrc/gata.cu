@@ -565,6 +565,33 @@ static int gata_check(int C, int H, int lmax, int V) {
   return 0;
 }
 
+// TMA-staged production variants (gata_staged.cu); *handled = false -> shape outside their contract
+int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, const float* x, const float* v,
+                    const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                    const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax, int flags,
+                    int max_deg_in, float* h_out, float* Xd_out, float* alpha, cudaStream_t st, bool* handled);
+
+int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
+                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                        const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax,
+                        int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe, int ldgz, float* da,
+                        cudaStream_t st, bool* handled);
+int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
+                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                        const float* alpha, const float* da, const int32_t* src_ptr, const int32_t* src_perm,
+                        const int32_t* tgt, int N, int C, int H, int lmax, int flags, float* g_qk, int ldgqk, float* g_x,
+                        float* g_v, float* g_Xd_in, cudaStream_t st, bool* handled);
+
+// GOTEN_GATA=legacy forces the register-gather kernels of this file (A/B timing, tests)
+static bool use_staged() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GOTEN_GATA");
+    v = (e && strcmp(e, "legacy") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
 }  // namespace goten
 
 using namespace goten;
@@ -613,6 +640,13 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
   if (gata_check(C, H, lmax, V)) return 1;
   if (N == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (use_staged()) {
+    bool handled = false;
+    if (gata_fwd_staged(h, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, tgt_ptr, src, N, C, H, lmax, flags, max_deg_in,
+                        h_out, Xd_out, alpha, st, &handled))
+      return 1;
+    if (handled) return 0;
+  }
   const int Dt = (C / H) / V, W = Dt < 32 ? Dt : 32, nparts = (C / V) / W, L = (lmax + 1) * (lmax + 1) - 1;
   if (max_deg_in < 1) max_deg_in = 1;
   const size_t smem = gata_smem_floats(max_deg_in, nparts, H, L, false) * sizeof(float);
@@ -632,6 +666,13 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
   if (gata_check(C, H, lmax, V)) return 1;
   if (N == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (use_staged() && g_fc == nullptr && g_Y == nullptr) {  // geometry gradients (forces) stay on the kernels below
+    bool handled = false;
+    if (gata_bwd_tgt_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H, lmax,
+                            flags, max_deg_in, g_qk, ldgqk, gZe, ldgz, da, st, &handled))
+      return 1;
+    if (handled) return 0;
+  }
   const int L = (lmax + 1) * (lmax + 1) - 1, S = multiplier_of(lmax, lmax > 1 ? flags : 0);
   const int g_cols = gcd_i(S * (C / H), 32 * V);  // column group that never straddles a head; multiple of V
   GOTEN_REQUIRE(g_cols % V == 0 && C % g_cols == 0, "unsupported head / channel combination (C=%d H=%d S=%d)", C, H, S);
@@ -654,6 +695,13 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
   if (gata_check(C, H, lmax, V)) return 1;
   if (N == 0) return 0;
   cudaStream_t st = as_stream(stream);
+  if (use_staged()) {
+    bool handled = false;
+    if (gata_bwd_src_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, da, src_ptr, src_perm, tgt, N, C,
+                            H, lmax, flags, g_qk, ldgqk, g_x, g_v, g_Xd_in, st, &handled))
+      return 1;
+    if (handled) return 0;
+  }
   const int L = (lmax + 1) * (lmax + 1) - 1;
   const size_t smem = (size_t)SRC_CHUNK * (4 + L + 2 * H) * sizeof(float);
   GATA_DISPATCH(gata_bwd_src_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, da,
