@@ -553,7 +553,7 @@ static int ring_depth() {
   static int r = 0;
   if (r == 0) {
     const char* e = getenv("GOTEN_GATA_STAGES");
-    r = e ? atoi(e) : 2;
+    r = e ? atoi(e) : 1;  // measured on B200 (cfg2): depth 1 wins, more resident CTAs beat a deeper ring
     if (r < 1) r = 1;
     if (r > 8) r = 8;
   }

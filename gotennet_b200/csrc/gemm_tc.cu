@@ -431,19 +431,51 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
-// B-operand preparation: hi = rna_tf32(b), lo = b - hi; optional transpose ([R][C] -> [C][R])
-__global__ void split_tf32_kernel(const float* __restrict__ in, int ld, int rows, int cols, int transpose,
+// B-operand preparation: hi = rna_tf32(b), lo = b - hi.
+// Row-wise form ([R][C] -> [R][C]): 128-bit loads/stores, grid-stride, no integer division per element.
+__global__ void split_tf32_vec4_kernel(const float* __restrict__ in, int ld, int rows, int cols4,
+                                       float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = (int64_t)rows * cols4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / cols4), c4 = (int)(idx - (int64_t)r * cols4);
+    const float4 v = *reinterpret_cast<const float4*>(in + (int64_t)r * ld + 4 * c4);
+    float4 h, l;
+    h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+    reinterpret_cast<float4*>(hi)[idx] = h;
+    reinterpret_cast<float4*>(lo)[idx] = l;
+  }
+}
+// scalar row-wise form for unaligned shapes
+__global__ void split_tf32_kernel(const float* __restrict__ in, int ld, int rows, int cols,
                                   float* __restrict__ hi, float* __restrict__ lo) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)rows * cols) return;
-  int r, c;
-  int64_t o;
-  if (!transpose) { r = (int)(idx / cols); c = (int)(idx % cols); o = idx; }
-  else { c = (int)(idx / rows); r = (int)(idx % rows); o = idx; }  // output [cols][rows], coalesced writes
+  const int r = (int)(idx / cols), c = (int)(idx - (int64_t)r * cols);
   const float v = in[(int64_t)r * ld + c];
   const float h = tf32_rna(v);
-  hi[o] = h;
-  lo[o] = v - h;
+  hi[idx] = h;
+  lo[idx] = v - h;
+}
+// transposing form ([R][C] -> [C][R]) through a 32x33 shared-memory tile: coalesced on both sides
+__global__ void split_tf32_transpose_kernel(const float* __restrict__ in, int ld, int rows, int cols,
+                                            float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int r = r0 + y, c = c0 + threadIdx.x;
+    tile[y][threadIdx.x] = (r < rows && c < cols) ? in[(int64_t)r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int y = threadIdx.y; y < 32; y += blockDim.y) {
+    const int c = c0 + y, r = r0 + threadIdx.x;  // output row = input column
+    if (c < cols && r < rows) {
+      const float v = tile[threadIdx.x][y];
+      const float h = tf32_rna(v);
+      hi[(int64_t)c * rows + r] = h;
+      lo[(int64_t)c * rows + r] = v - h;
+    }
+  }
 }
 
 }  // namespace tc
@@ -587,7 +619,16 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
     else if (trans_b) { rows = N; cols = K; transpose = 0; b_ld = K; }          // B[N][K] -> hi/lo [N][K]
     else { rows = K; cols = N; transpose = 1; b_ld = K; }                        // B[K][N] -> hi/lo [N][K]
     const int64_t tot = (int64_t)rows * cols;
-    tc::split_tf32_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(B, ldb, rows, cols, transpose, Bh, Bl);
+    if (transpose) {
+      dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32)), block(32, 8);
+      tc::split_tf32_transpose_kernel<<<grid, block, 0, st>>>(B, ldb, rows, cols, Bh, Bl);
+    } else if (cols % 4 == 0 && ldb % 4 == 0) {  // B is 16 B aligned (checked above)
+      const int64_t tot4 = tot / 4;
+      const unsigned grid = (unsigned)(cdiv64(tot4, 256) < (int64_t)sm_count * 16 ? cdiv64(tot4, 256) : (int64_t)sm_count * 16);
+      tc::split_tf32_vec4_kernel<<<grid, 256, 0, st>>>(B, ldb, rows, cols / 4, Bh, Bl);
+    } else {
+      tc::split_tf32_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(B, ldb, rows, cols, Bh, Bl);
+    }
     GOTEN_CHECK_LAUNCH();
   }
 
