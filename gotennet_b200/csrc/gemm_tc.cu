@@ -22,9 +22,9 @@ namespace goten {
 
 namespace tc {
 
-constexpr int BM = 128;          // UMMA M
+constexpr int BM = 128;          // UMMA M per CTA (cta_group::2: the pair computes M = 256)
 constexpr int BK = 32;           // floats per k-block = one 128 B swizzle row
-constexpr int STAGES = 2;
+constexpr int MAX_STAGES = 4;    // smem ring depth is chosen by the host (Params::stages)
 constexpr int NTHREADS = 320;
 constexpr int EPI_WARP0 = 2, CONV_WARP0 = 6;
 
@@ -89,6 +89,46 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: one MMA spans two SMs (M = 256), each CTA stages its own 128 rows of A and
+// half of the B tile; barriers that gate the issuing (leader) CTA receive remote arrives from the peer.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default (.release.cta)
+// semantics as in CUTLASS' ClusterBarrier::arrive: the explicit .release.cluster form compiles to MEMBAR + ERRBAR
+// and cost 17 % of all stall samples on the converter's critical path (profiles/r1f).
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+      "}" ::"r"(bar),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// completion of all prior MMAs -> arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2cta(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -127,6 +167,8 @@ struct Params {
   int block_n;            // UMMA N (64 / 128 / 256)
   int n_mt, n_nt;         // tiles
   int splits, kb_per_split, kb_total;
+  int stages;             // smem ring depth (<= MAX_STAGES)
+  int dbg;                // GOTEN_GEMM_DBG experiment switches (timing only; results are wrong when set)
   float* C; int ldc;
   const float* bias;
   const float* add_src; int ld_add;
@@ -137,44 +179,54 @@ struct Params {
   float* partial_colsum;  // [splits][M]
 };
 
-template <bool MN_MAJOR>
+template <bool MN_MAJOR, int NCTA>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int BN = p.block_n;
+  const int BN = p.block_n;                        // UMMA N (whole tile width)
+  const int BNH = BN / NCTA;                       // B rows staged by this CTA
+  const int STAGES = p.stages;
   const uint32_t A_BYTES = BM * BK * 4;            // 16 KB
-  const uint32_t B_BYTES = (uint32_t)BN * BK * 4;  // <= 32 KB
+  const uint32_t B_BYTES = (uint32_t)BNH * BK * 4; // <= 32 KB
   const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;                    // 4 warps x 2 x [32 rows][128 B], 128B-swizzled
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * 2 * 4096);
-  // bars: full[S], conv[S], empty[S], tmem_full[2], tmem_empty[2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 4);
-  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + STAGES), bar_empty = smem_u32(bars + 2 * STAGES);
-  const uint32_t bar_tfull = smem_u32(bars + 3 * STAGES), bar_tempty = smem_u32(bars + 3 * STAGES + 2);
+  // bars: full[MAX_STAGES], conv[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + MAX_STAGES), bar_empty = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 3 * MAX_STAGES), bar_tempty = smem_u32(bars + 3 * MAX_STAGES + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;   // rank 0 = leader: issues the MMAs
+  const int unit = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // persistent work-unit id
+  const int n_units = NCTA == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 4);   // one arrive per converter warp
+      mbar_init(bar_conv + 8 * s, 4 * NCTA);   // one arrive per converter warp (of both CTAs: leader's barrier)
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);  // one arrive per epilogue warp
+      mbar_init(bar_tempty + 8 * a, 4 * NCTA);  // one arrive per epilogue warp (of both CTAs: leader's barrier)
     }
     fence_barrier_init();
   }
   if (warp == 1) {  // TMEM: 512 columns = two accumulator stages of up to 256 columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -185,9 +237,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // =============================== TMA producer ===============================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+      for (int w = unit; w < n_items; w += n_units) {
         const int split = w / n_tiles, tile = w % n_tiles;
-        const int m0 = (tile / p.n_nt) * BM, n0 = (tile % p.n_nt) * BN;
+        const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN + (int)rank * BNH;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -211,16 +263,16 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((MN_MAJOR ? 1u : 0u) << 15) |
-                             ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((MN_MAJOR ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
       // K-major: 8-row groups 1024 B apart, k-step = +32 B.  MN-major: 32-wide MN chunks BK*128 B apart (LBO),
       // 8-deep k atoms 1024 B apart (SBO), k-step = +1024 B.
       // MN-major uses the 32B-base swizzle: k atoms are 4 rows (512 B) deep, two per K=8 instruction.
       const uint32_t lbo = MN_MAJOR ? BK * 128 : 16, sbo = MN_MAJOR ? 512 : 1024, kstep = MN_MAJOR ? 1024 : 32;
       const uint32_t lt = MN_MAJOR ? 1 : 2;
       uint32_t it = 0, tile_it = 0;
-      for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
+      for (int w = unit; w < n_items; w += n_units, ++tile_it) {
         const int split = w / n_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -231,7 +283,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
           mbar_wait(bar_full + 8 * s, ph);
-          mbar_wait(bar_conv + 8 * s, ph);
+          mbar_wait(bar_conv + 8 * s, ph);   // converters of both CTAs: implies the peer's TMA data has landed too
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
           const uint32_t sal = sa + A_BYTES, sbh = sa + 2 * A_BYTES, sbl = sbh + B_BYTES;
@@ -239,22 +291,29 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t a_hi = make_desc(sa + kk * kstep, lbo, sbo, lt), a_lo = make_desc(sal + kk * kstep, lbo, sbo, lt);
             const uint64_t b_hi = make_desc(sbh + kk * kstep, lbo, sbo, lt), b_lo = make_desc(sbl + kk * kstep, lbo, sbo, lt);
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            if (NCTA == 2) {
+              umma_tf32_2cta(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              if (!(p.dbg & 1)) umma_tf32_2cta(d_tmem, a_hi, b_lo, idesc, 1u);
+              if (!(p.dbg & 2)) umma_tf32_2cta(d_tmem, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_tf32(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              if (!(p.dbg & 1)) umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+              if (!(p.dbg & 2)) umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
           }
-          umma_commit(bar_empty + 8 * s);  // smem stage reusable once these MMAs have read it
+          // smem stage reusable (in both CTAs) once these MMAs have read it
+          if (NCTA == 2) umma_commit_2cta(bar_empty + 8 * s); else umma_commit(bar_empty + 8 * s);
         }
-        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        if (NCTA == 2) umma_commit_2cta(bar_tfull + 8 * acc); else umma_commit(bar_tfull + 8 * acc);  // accumulator complete
       }
     }
   } else if (warp >= CONV_WARP0) {
     // =============================== converter ==================================
     const int ct = threadIdx.x - CONV_WARP0 * 32;  // 0..127
     uint32_t it = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x) {
+    for (int w = unit; w < n_items; w += n_units) {
       const int split = w / n_tiles, tile = w % n_tiles;
-      const int m0 = (tile / p.n_nt) * BM;
+      const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM;
       const bool do_cs = MN_MAJOR && (p.colsum != nullptr) && (tile % p.n_nt == 0);
       const int kb0 = split * p.kb_per_split;
       const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -294,7 +353,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(bar_conv + 8 * s, 0);  // the leader's barrier gates the MMA issue
+          else mbar_arrive(bar_conv + 8 * s);
+        }
       }
       if (do_cs) {
         const int m = m0 + ct;
@@ -315,9 +377,9 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     uint8_t* my_buf = epi_smem + (warp - EPI_WARP0) * 2 * 4096;
     const bool fast = (p.add_src == nullptr) && (p.act_out == nullptr);
     uint32_t tile_it = 0, n_store = 0;
-    for (int w = blockIdx.x; w < n_items; w += gridDim.x, ++tile_it) {
+    for (int w = unit; w < n_items; w += n_units, ++tile_it) {
       const int split = w / n_tiles, tile = w % n_tiles;
-      const int m0 = (tile / p.n_nt) * BM, n0 = (tile % p.n_nt) * BN;
+      const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN;
       const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
       mbar_wait(bar_tfull + 8 * acc, aph);
       tc_fence_after();
@@ -418,16 +480,20 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
     }
     if (fast && lane == 0) bulk_wait_all();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal / read this CTA until here
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
   }
 }
 
@@ -535,6 +601,8 @@ struct TcPlan {
   bool ok;
   bool mn_major;
   int block_n, n_mt, n_nt, splits, kb_total, kb_per_split;
+  int ncta;              // 1, or 2 = CTA pair (tcgen05 cta_group::2, M = 256 per MMA)
+  int stages;
   int64_t b_elems;       // elements of each pre-split B copy
   int64_t ws_bytes;
 };
@@ -549,7 +617,16 @@ static TcPlan tc_plan(int M, int N, int K, int trans_a, int trans_b) {
   if (t.mn_major && (M % 32 != 0 || N % 32 != 0)) return t;
   if (N < 16) return t;
   t.block_n = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  t.n_mt = (M + tc::BM - 1) / tc::BM;
+  // CTA pairs halve the B bytes each SM stages and feeds to its tensor core per FLOP (the kernel is bound by
+  // shared-memory bandwidth, profiles/r1d): used whenever there are enough 256-row tiles to fill the pairs.
+  // GOTEN_GEMM_NCTA=1 forces single-CTA MMAs.
+  static int force_ncta = -1;
+  if (force_ncta < 0) { const char* e = getenv("GOTEN_GEMM_NCTA"); force_ncta = e ? atoi(e) : 0; }
+  t.ncta = (force_ncta == 1) ? 1 : ((M >= 512 || force_ncta == 2) ? 2 : 1);
+  const size_t stage_bytes = 2 * (size_t)tc::BM * tc::BK * 4 + 2 * (size_t)(t.block_n / t.ncta) * tc::BK * 4;
+  t.stages = (int)((232448 - 4 * 2 * 4096 - 1024 - 256) / stage_bytes);  // 227 KB opt-in limit
+  if (t.stages > tc::MAX_STAGES) t.stages = tc::MAX_STAGES;
+  t.n_mt = (M + tc::BM * t.ncta - 1) / (tc::BM * t.ncta);
   t.n_nt = (N + t.block_n - 1) / t.block_n;
   t.kb_total = (K + tc::BK - 1) / tc::BK;
   t.splits = 1;
@@ -560,7 +637,7 @@ static TcPlan tc_plan(int M, int N, int K, int trans_a, int trans_b) {
     // summed with round-to-nearest by the split-K reduction kernel.
     constexpr int MAX_CHAIN_KB = 48;
     const int tiles = t.n_mt * t.n_nt;
-    int want = 148 / tiles;  // at least one wave of (tile, split) work items
+    int want = (148 / t.ncta) / tiles;  // at least one wave of (tile, split) work items
     if (want < 1) want = 1;
     int per = (t.kb_total + want - 1) / want;
     if (per > MAX_CHAIN_KB) per = MAX_CHAIN_KB;
@@ -635,11 +712,11 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
   CUtensorMap mA, mBh, mBl, mC;
   bool ok;
   if (!t.mn_major) {
-    ok = make_map_kmajor(&mA, A, lda, M, K, tc::BM) && make_map_kmajor(&mBh, Bh, b_ld, N, K, t.block_n) &&
-         make_map_kmajor(&mBl, Bl, b_ld, N, K, t.block_n);
+    ok = make_map_kmajor(&mA, A, lda, M, K, tc::BM) && make_map_kmajor(&mBh, Bh, b_ld, N, K, t.block_n / t.ncta) &&
+         make_map_kmajor(&mBl, Bl, b_ld, N, K, t.block_n / t.ncta);
   } else {
-    ok = make_map_mnmajor(&mA, A, lda, K, M, tc::BM) && make_map_mnmajor(&mBh, Bh, b_ld, K, N, t.block_n) &&
-         make_map_mnmajor(&mBl, Bl, b_ld, K, N, t.block_n);
+    ok = make_map_mnmajor(&mA, A, lda, K, M, tc::BM) && make_map_mnmajor(&mBh, Bh, b_ld, K, N, t.block_n / t.ncta) &&
+         make_map_mnmajor(&mBl, Bl, b_ld, K, N, t.block_n / t.ncta);
   }
   GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
   // output map for the TMA-store epilogue: 32 x 32 blocks of C (or of the split-K partial buffer)
@@ -655,6 +732,12 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
   p.M = M; p.N = N; p.K = K;
   p.block_n = t.block_n; p.n_mt = t.n_mt; p.n_nt = t.n_nt;
   p.splits = t.splits; p.kb_per_split = t.kb_per_split; p.kb_total = t.kb_total;
+  p.stages = t.stages;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("GOTEN_GEMM_DBG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+  }
   p.C = C; p.ldc = ldc; p.bias = bias; p.add_src = add_src; p.ld_add = ld_add;
   p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
   p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
@@ -662,20 +745,36 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
   p.partial = partial; p.colsum = colsum; p.partial_colsum = partial_cs;
   if (t.splits > 1) { p.bias = nullptr; p.add_src = nullptr; p.act_out = nullptr; }  // applied by splitk_finish
 
-  const size_t smem = 1024 + (size_t)tc::STAGES * (2 * tc::BM * tc::BK * 4 + 2 * (size_t)t.block_n * tc::BK * 4) +
-                      4 * 2 * 4096 + (3 * tc::STAGES + 4) * 8 + 16;
+  const size_t smem = 1024 + (size_t)t.stages * (2 * tc::BM * tc::BK * 4 + 2 * (size_t)(t.block_n / t.ncta) * tc::BK * 4) +
+                      4 * 2 * 4096 + (3 * tc::MAX_STAGES + 4) * 8 + 16;
   GOTEN_REQUIRE((int)smem <= smem_optin, "tcgen05 GEMM needs %zu B of shared memory", smem);
   const int n_items = t.n_mt * t.n_nt * t.splits;
-  const int grid = n_items < sm_count ? n_items : sm_count;
+  const int max_units = sm_count / t.ncta;
+  const int grid = (n_items < max_units ? n_items : max_units) * t.ncta;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tc::NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)t.ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define GOTEN_TC_LAUNCH(MN, NC)                                                                             \
+  do {                                                                                                      \
+    auto k = tc::gemm3x_kernel<MN, NC>;                                                                     \
+    GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, p));                                     \
+  } while (0)
   if (t.mn_major) {
-    auto k = tc::gemm3x_kernel<true>;
-    GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, tc::NTHREADS, smem, st>>>(mA, mBh, mBl, mC, p);
+    if (t.ncta == 2) GOTEN_TC_LAUNCH(true, 2); else GOTEN_TC_LAUNCH(true, 1);
   } else {
-    auto k = tc::gemm3x_kernel<false>;
-    GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, tc::NTHREADS, smem, st>>>(mA, mBh, mBl, mC, p);
+    if (t.ncta == 2) GOTEN_TC_LAUNCH(false, 2); else GOTEN_TC_LAUNCH(false, 1);
   }
+#undef GOTEN_TC_LAUNCH
   GOTEN_CHECK_LAUNCH();
   if (t.splits > 1) {
     if (splitk_finish(partial, partial_cs, t.splits, C, ldc, M, N, bias, add_src, ld_add, act_out, ld_act, act_lo,
