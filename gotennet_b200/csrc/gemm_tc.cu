@@ -324,31 +324,41 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint8_t* a_raw = smem + s * STAGE_BYTES;
         uint8_t* a_lo = a_raw + A_BYTES;
         if (!MN_MAJOR) {
-          // thread = tile row; rotate the 16 B chunk order so a quarter warp hits 8 distinct bank groups
+          // thread = tile row; rotate the 16 B chunk order so a quarter warp hits 8 distinct bank groups.
+          // All eight loads are issued before the first store (the in-place stores would otherwise fence them).
+          float4 v[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = *reinterpret_cast<const float4*>(a_raw + ct * 128 + (((c + ct) & 7) << 4));
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
             const int pc = (c + ct) & 7;
-            float4* ph_ = reinterpret_cast<float4*>(a_raw + ct * 128 + pc * 16);
-            float4* pl_ = reinterpret_cast<float4*>(a_lo + ct * 128 + pc * 16);
-            const float4 v = *ph_;
             float4 h, l;
-            h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-            *ph_ = h;
-            *pl_ = l;
+            h.x = tf32_rna(v[c].x); h.y = tf32_rna(v[c].y); h.z = tf32_rna(v[c].z); h.w = tf32_rna(v[c].w);
+            l.x = v[c].x - h.x; l.y = v[c].y - h.y; l.z = v[c].z - h.z; l.w = v[c].w - h.w;
+            *reinterpret_cast<float4*>(a_raw + ct * 128 + pc * 16) = h;
+            *reinterpret_cast<float4*>(a_lo + ct * 128 + pc * 16) = l;
           }
         } else {
           // thread = logical MN column (chunk = ct/32, col = ct%32); walks the 32 k rows of the chunk
           const int chunk = ct >> 5, col = ct & 31;
           const int cw = col >> 3, wi = col & 7;  // 32 B chunk index / word inside it (SWIZZLE_128B_ATOM_32B)
-#pragma unroll 8
-          for (int k = 0; k < BK; ++k) {
-            const int off = chunk * (BK * 128) + k * 128 + ((cw ^ (k & 3)) << 5) + wi * 4;
-            const float v = *reinterpret_cast<float*>(a_raw + off);
-            const float h = tf32_rna(v);
-            *reinterpret_cast<float*>(a_raw + off) = h;
-            *reinterpret_cast<float*>(a_lo + off) = v - h;
-            csum += v;
+#pragma unroll
+          for (int k0 = 0; k0 < BK; k0 += 8) {  // batches of 8 loads ahead of the in-place stores
+            float v[8];
+            int off[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int k = k0 + u;
+              off[u] = chunk * (BK * 128) + k * 128 + ((cw ^ (k & 3)) << 5) + wi * 4;
+              v[u] = *reinterpret_cast<const float*>(a_raw + off[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float h = tf32_rna(v[u]);
+              *reinterpret_cast<float*>(a_raw + off[u]) = h;
+              *reinterpret_cast<float*>(a_lo + off[u]) = v[u] - h;
+              csum += v[u];
+            }
           }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -622,7 +632,7 @@ static TcPlan tc_plan(int M, int N, int K, int trans_a, int trans_b) {
   // GOTEN_GEMM_NCTA=1 forces single-CTA MMAs.
   static int force_ncta = -1;
   if (force_ncta < 0) { const char* e = getenv("GOTEN_GEMM_NCTA"); force_ncta = e ? atoi(e) : 0; }
-  t.ncta = (force_ncta == 1) ? 1 : ((M >= 512 || force_ncta == 2) ? 2 : 1);
+  t.ncta = (force_ncta == 1) ? 1 : ((M >= 256 || force_ncta == 2) ? 2 : 1);
   const size_t stage_bytes = 2 * (size_t)tc::BM * tc::BK * 4 + 2 * (size_t)(t.block_n / t.ncta) * tc::BK * 4;
   t.stages = (int)((232448 - 4 * 2 * 4096 - 1024 - 256) / stage_bytes);  // 227 KB opt-in limit
   if (t.stages > tc::MAX_STAGES) t.stages = tc::MAX_STAGES;
@@ -766,7 +776,11 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
 #define GOTEN_TC_LAUNCH(MN, NC)                                                                             \
   do {                                                                                                      \
     auto k = tc::gemm3x_kernel<MN, NC>;                                                                     \
-    GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    static int smem_set = 0; /* per instantiation: the attribute call takes a context lock, do it once */   \
+    if ((int)smem > smem_set) {                                                                             \
+      GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));   \
+      smem_set = smem_optin;                                                                                \
+    }                                                                                                       \
     GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, p));                                     \
   } while (0)
   if (t.mn_major) {

@@ -237,6 +237,28 @@ int goten_embedding_fwd(const float* table, const int64_t* idx, int64_t n, int C
 int goten_embedding_bwd(const float* g_out, const int64_t* idx, int64_t n, int C, int n_rows,
                         float* g_table, float* workspace, int64_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------- read-out head --
+ * Atomwise.forward (models/components/outputs.py:323-376): per-atom MLP output `raw`
+ * [N][n_out] -> ScaleShift (components/layers.py:172-202, mean/stddev with 1 or n_out
+ * entries, nullable) -> + atomref[z] (outputs.py:349-351, nullable) -> yi [N][n_out];
+ * torch_scatter.scatter(yi, batch, reduce=mode) (outputs.py:354-355) -> y [n_mol][n_out]
+ * as a deterministic segmented reduction over mol_ptr.  mode: 0 none, 1 sum, 2 mean.
+ * goten_mol_ptr builds mol_ptr [n_mol+1] from the (sorted) int64 batch vector of a PyG
+ * batch; unsorted_flag[0] (device, nullable) is set to 1 when the vector is not sorted.
+ * goten_act_*: the head MLP's activations (layers.py:69-81, :619): kind 1 SiLU, 2 shifted
+ * softplus.                                                                          */
+int goten_mol_ptr(const int64_t* batch, int n_nodes, int n_mol, int32_t* mol_ptr, int32_t* unsorted_flag,
+                  void* stream);
+int goten_atomwise_reduce_fwd(const float* raw, const int64_t* z, const float* atomref, int atomref_rows,
+                              const float* mean, const float* stddev, int n_stat, const int32_t* mol_ptr,
+                              int n_nodes, int n_mol, int n_out, int mode, float* yi, float* y,
+                              void* stream);
+int goten_atomwise_reduce_bwd(const float* g_y, const float* g_yi, const float* stddev, int n_stat,
+                              const int32_t* mol_ptr, int n_nodes, int n_mol, int n_out, int mode,
+                              float* g_raw, void* stream);
+int goten_act_fwd(int kind, const float* x, int64_t n, float* y, void* stream);
+int goten_act_bwd(int kind, const float* g, const float* x, int64_t n, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,7 @@ Only a handful of their symbols are touched on the hot path:
   torch_cluster.radius_graph               layers.py:15
   pytorch_lightning.utilities.rank_zero_only  utils/__init__.py:6
   omegaconf.DictConfig / OmegaConf         utils/__init__.py:5
+  torch_scatter.scatter, ase               components/outputs.py:3,6 (Atomwise read-out head)
 
 The stand-ins below restate the *published* semantics of those symbols
 (PyG 2.x, torch_cluster 1.6 CUDA build):
@@ -231,6 +232,21 @@ def install() -> None:
 
     oc.DictConfig, oc.OmegaConf = DictConfig, OmegaConf
     sys.modules["omegaconf"] = oc
+
+    # read-out heads (models/components/outputs.py:3,6): torch_scatter.scatter and an `ase` placeholder
+    # (ase.data.atomic_masses is only touched by ElectronicSpatialExtentV2, outputs.py:513 -- not on our path)
+    ts = types.ModuleType("torch_scatter")
+    ts.scatter = lambda src, index, dim=0, out=None, dim_size=None, reduce="sum": _scatter(
+        src, index, dim=dim, dim_size=dim_size, reduce=reduce)
+    sys.modules["torch_scatter"] = ts
+    ase = types.ModuleType("ase")
+    ase_data = types.ModuleType("ase.data")
+    import numpy as _np
+
+    ase_data.atomic_masses = _np.zeros(119)
+    ase.data = ase_data
+    sys.modules["ase"] = ase
+    sys.modules["ase.data"] = ase_data
 
 
 def import_reference(path: str = "/root/reference"):
