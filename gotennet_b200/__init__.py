@@ -11,3 +11,4 @@ __version__ = "0.1.0"
 from ._lib import GotenError  # noqa: F401
 from .gotennet import EQFF, GATA, GotenNet, GotenNetWrapper  # noqa: F401
 from .layers import CosineCutoff, Dense, Distance, ExpNormalSmearing, MLP, TensorInit  # noqa: F401
+from .outputs import Atomwise, ScaleShift, SchnetMLP, shifted_softplus  # noqa: F401

@@ -128,6 +128,7 @@ class PermuteFn(torch.autograd.Function):
         return permute_nlc(x.contiguous(), to_dm)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         return permute_nlc(g.contiguous(), not ctx.to_dm), None
 
@@ -146,6 +147,7 @@ class EmbeddingFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
         g = g.contiguous()
@@ -187,6 +189,7 @@ class EdgeGeometryFn(torch.autograd.Function):
         return r, Y, fc, phi, u, kappa
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_r, g_Y, g_fc, g_phi, _gu, _gk):
         r, u, means, betas = ctx.saved_tensors
         plan = ctx.plan
@@ -241,6 +244,7 @@ class InitBlockFn(torch.autograd.Function):
         return h, t
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_h, g_t):
         hnbr, phi, fc, Wphi, W1, ln_g, ln_b, W2, F, ctx0, y1, y2, mean, rstd, h = ctx.saved_tensors
         plan = ctx.plan
@@ -349,6 +353,7 @@ class GataBlockFn(torch.autograd.Function):
         return h1, Xd1  # last layer: t_ij passes through unchanged (gotennet.py:449-450)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_h1, g_Xd1, g_t1=None):
         (h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK) = ctx.saved_tensors
         plan, cfg, htr = ctx.plan, ctx.cfg, ctx.htr
@@ -463,6 +468,7 @@ class EqffBlockFn(torch.autograd.Function):
         return h2, Xd2
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, g_h2, g_Xd2):
         Xd, Wvu, Wm1, Wm2, P, cx, Zm, Am, M = ctx.saved_tensors
         L_ = lib()
@@ -486,3 +492,95 @@ class EqffBlockFn(torch.autograd.Function):
         dWvu = torch.empty_like(Wvu)
         gemm(g_P, C, 1, Xd, C, 0, dWvu, C, C, C, L * N)
         return g_h, g_Xd, dWvu, dWm1, dbm1, dWm2, dbm2, None
+
+
+# ---------------------------------------------------------------------------
+# read-out head (reference models/components/outputs.py:232-376)
+# ---------------------------------------------------------------------------
+ACT_NONE, ACT_SILU, ACT_SSP = 0, 1, 2
+
+
+class DenseActFn(torch.autograd.Function):
+    """y = act(x W^T + b) for the head MLP (components/layers.py:225-273 SchnetMLP of Dense layers).
+    SiLU rides in the GEMM epilogue; shifted softplus (layers.py:69-81) is one element-wise kernel."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, kind):
+        _chk(x, w, b)
+        x, w = _f32(x.contiguous()), w.contiguous()
+        ctx.kind, ctx.has_bias = kind, b is not None
+        if kind == ACT_SILU:
+            z, y = linear_fwd(x, w, b, act=True)
+        else:
+            z = linear_fwd(x, w, b)
+            y = z
+            if kind == ACT_SSP:
+                y = torch.empty_like(z)
+                lib().call("goten_act_fwd", kind, _ptr(z), z.numel(), _ptr(y), _stream())
+        ctx.save_for_backward(x, w, z)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, w, z = ctx.saved_tensors
+        g = g.contiguous()
+        if ctx.kind != ACT_NONE:
+            gz = torch.empty_like(g)
+            lib().call("goten_act_bwd", ctx.kind, _ptr(g), _ptr(z), g.numel(), _ptr(gz), _stream())
+            g = gz
+        da, dw, db = linear_bwd(g, x, w, need_da=ctx.needs_input_grad[0], need_bias=ctx.has_bias)
+        return da, dw, db, None
+
+
+def mol_ptr_from_batch(batch: torch.Tensor, n_mol: int, check_sorted: bool = True) -> torch.Tensor:
+    """[n_mol+1] int32 atom offsets of the molecules of a (sorted) PyG batch vector."""
+    _chk(batch)
+    batch = batch.contiguous().long()
+    mol_ptr = torch.empty(n_mol + 1, dtype=torch.int32, device=batch.device)
+    flag = torch.empty(1, dtype=torch.int32, device=batch.device) if check_sorted else None
+    lib().call("goten_mol_ptr", _ptr(batch), batch.numel(), n_mol, _ptr(mol_ptr), _ptr(flag), _stream())
+    if check_sorted and int(flag.item()) != 0:
+        raise GotenError("the batch vector must be sorted by molecule id (PyG batches are)")
+    return mol_ptr
+
+
+class AtomwiseReduceFn(torch.autograd.Function):
+    """raw [N,n_out] -> yi = raw*stddev + mean (+ atomref[z]);  y = segment sum / mean over molecules
+    (outputs.py:347-355).  mode: 0 none, 1 sum, 2 mean."""
+
+    @staticmethod
+    def forward(ctx, raw, z, atomref, mean, stddev, mol_ptr, n_mol, mode):
+        _chk(raw, z, atomref, mean, stddev, mol_ptr)
+        raw = _f32(raw.contiguous())
+        N, n_out = raw.shape
+        dev = raw.device
+        n_stat = stddev.numel() if stddev is not None else (mean.numel() if mean is not None else 1)
+        yi = torch.empty_like(raw)
+        y = torch.zeros(n_mol, n_out, device=dev) if mode != 0 else None
+        lib().call("goten_atomwise_reduce_fwd", _ptr(raw), _ptr(z), _ptr(atomref),
+                   atomref.shape[0] if atomref is not None else 0, _ptr(mean), _ptr(stddev), n_stat, _ptr(mol_ptr), N,
+                   n_mol, n_out, mode, _ptr(yi), _ptr(y), _stream())
+        ctx.mode, ctx.n_mol, ctx.n_stat, ctx.N = mode, n_mol, n_stat, N
+        ctx.save_for_backward(stddev, mol_ptr)
+        if mode == 0:
+            return yi, yi
+        return yi, y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_yi, g_y):
+        stddev, mol_ptr = ctx.saved_tensors
+        if ctx.mode == 0:
+            g = g_yi if g_y is None else (g_y if g_yi is None else g_yi + g_y)
+            if stddev is not None:
+                g = g * stddev
+            return g, None, None, None, None, None, None, None
+        ref = g_yi if g_yi is not None else g_y
+        N = ctx.N
+        n_out = ref.shape[1]
+        g_raw = torch.zeros(N, n_out, device=ref.device)
+        lib().call("goten_atomwise_reduce_bwd", _ptr(g_y.contiguous() if g_y is not None else None),
+                   _ptr(g_yi.contiguous() if g_yi is not None else None), _ptr(stddev), ctx.n_stat, _ptr(mol_ptr), N,
+                   ctx.n_mol, n_out, ctx.mode, _ptr(g_raw), _stream())
+        return g_raw, None, None, None, None, None, None, None

@@ -1,0 +1,159 @@
+"""Read-out head of the path's next row: `Atomwise` energy head with optional
+forces, reference models/components/outputs.py:232-376 (+ SchnetMLP components/layers.py:225-273,
+ScaleShift :172-202, GetItem :205-222, shifted_softplus :69-81).
+
+Same constructor signature, attribute names and state_dict keys as the reference
+(`atomref.weight`, `out_net.1.out_net.{i}.{weight,bias}`, `standardize.{mean,stddev}`), so a
+reference checkpoint's `output_modules.0.*` entries load unchanged.  The per-atom MLP runs on
+the tcgen05 / SIMT GEMM kernels (SiLU fused in the epilogue), standardisation + atomref +
+the per-molecule sum is one deterministic segmented-reduction kernel (the reference scatters
+with atomics), and forces come from the hand-written backward of the interaction block.
+
+Not implemented (raises): equivariant out-nets (`GatedEquivariantBlock` heads used by Dipole /
+ElectronicSpatialExtentV2), and second-order autograd through the block -- `create_graph=True`
+(the reference default, outputs.py:248) still yields correct first-order forces, but
+back-propagating *through* them (force-loss training) raises instead of silently dropping terms.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.autograd import grad
+
+from . import ops
+from ._lib import GotenError
+from .layers import Dense, ShiftedSoftplus, is_silu, str2act
+
+
+def shifted_softplus(x: torch.Tensor):
+    """ln(1 + exp(x)) - ln 2 (reference layers.py:69-81)."""
+    return F.softplus(x) - math.log(2.0)
+
+
+def _act_kind(act) -> int:
+    if act is None:
+        return ops.ACT_NONE
+    if is_silu(act):
+        return ops.ACT_SILU
+    if act is shifted_softplus or isinstance(act, ShiftedSoftplus):
+        return ops.ACT_SSP
+    raise NotImplementedError(f"head activation {act!r}: the kernels implement SiLU and shifted softplus")
+
+
+class ScaleShift(nn.Module):
+    """y = x * stddev + mean (reference layers.py:172-202); fused into the read-out kernel by Atomwise."""
+
+    def __init__(self, mean, stddev):
+        super().__init__()
+        if isinstance(mean, float):
+            mean = torch.FloatTensor([mean])
+        if isinstance(stddev, float):
+            stddev = torch.FloatTensor([stddev])
+        self.register_buffer("mean", mean)
+        self.register_buffer("stddev", stddev)
+
+    def forward(self, input):
+        return input * self.stddev + self.mean
+
+
+class GetItem(nn.Module):
+    """inputs[key] / inputs.key (reference layers.py:205-222)."""
+
+    def __init__(self, key):
+        super().__init__()
+        self.key = key
+
+    def forward(self, inputs):
+        return inputs[self.key] if isinstance(inputs, dict) else getattr(inputs, self.key)
+
+
+class SchnetMLP(nn.Module):
+    """Pyramidal MLP of Dense layers (reference layers.py:225-273)."""
+
+    def __init__(self, n_in, n_out, n_hidden=None, n_layers=2, activation=shifted_softplus):
+        super().__init__()
+        if n_hidden is None:
+            c, self.n_neurons = n_in, []
+            for _ in range(n_layers):
+                self.n_neurons.append(c)
+                c = c // 2
+            self.n_neurons.append(n_out)
+        else:
+            if type(n_hidden) is int:
+                n_hidden = [n_hidden] * (n_layers - 1)
+            self.n_neurons = [n_in] + n_hidden + [n_out]
+        layers = [Dense(self.n_neurons[i], self.n_neurons[i + 1], activation=activation) for i in range(n_layers - 1)]
+        layers.append(Dense(self.n_neurons[-2], self.n_neurons[-1], activation=None))
+        self.out_net = nn.Sequential(*layers)
+
+    def forward(self, inputs):
+        x = inputs
+        for layer in self.out_net:
+            if layer.norm is not None:
+                raise NotImplementedError("normalised Dense layers are not part of the read-out path")
+            x = ops.DenseActFn.apply(x, layer.weight, layer.bias, _act_kind(layer.activation))
+        return x
+
+
+_MODES = {None: 0, "sum": 1, "add": 1, "mean": 2, "avg": 2}
+
+
+class Atomwise(nn.Module):
+    """Per-atom property -> per-molecule property (reference outputs.py:232-376)."""
+
+    def __init__(self, n_in: int, n_out: int = 1, aggregation_mode: Optional[str] = "sum", n_layers: int = 2,
+                 n_hidden: Optional[int] = None, activation=shifted_softplus, property: str = "y",
+                 contributions: Optional[str] = None, derivative: Optional[str] = None, negative_dr: bool = True,
+                 create_graph: bool = True, mean: Optional[torch.Tensor] = None, stddev: Optional[torch.Tensor] = None,
+                 atomref: Optional[torch.Tensor] = None, outnet: Optional[nn.Module] = None,
+                 return_vector: Optional[str] = None, standardize: bool = True):
+        super().__init__()
+        if aggregation_mode not in _MODES:
+            raise NotImplementedError(f"aggregation_mode {aggregation_mode!r}: sum / mean / None are implemented")
+        self.return_vector, self.n_layers, self.create_graph = return_vector, n_layers, create_graph
+        self.property, self.contributions, self.derivative = property, contributions, derivative
+        self.negative_dr = negative_dr
+        mean = torch.FloatTensor([0.0]) if mean is None else mean
+        stddev = torch.FloatTensor([1.0]) if stddev is None else stddev
+        if type(activation) is str:
+            activation = str2act(activation)
+        self.atomref = nn.Embedding.from_pretrained(atomref.type(torch.float32)) if atomref is not None else None
+        self.equivariant = False
+        if outnet is not None:
+            raise NotImplementedError("custom / equivariant out-nets are outside the accelerated read-out path")
+        self.out_net = nn.Sequential(GetItem("representation"), SchnetMLP(n_in, n_out, n_hidden, n_layers, activation))
+        self.standardize = ScaleShift(mean, stddev) if standardize else nn.Identity()
+        self.aggregation_mode = aggregation_mode
+
+    def forward(self, inputs):
+        z = inputs.z
+        result = {}
+        raw = self.out_net(inputs)  # [N, n_out]
+        if not raw.is_cuda:
+            raise GotenError("gotennet_b200 kernels need CUDA tensors (there is no CPU path)")
+        mode = _MODES[self.aggregation_mode]
+        mol_ptr, n_mol = None, 0
+        if mode != 0:
+            n_mol = getattr(inputs, "num_graphs", None)
+            if n_mol is None:  # same host read torch_scatter does to size its output
+                n_mol = int(inputs.batch[-1].item()) + 1 if inputs.batch.numel() else 0
+            mol_ptr = ops.mol_ptr_from_batch(inputs.batch, int(n_mol))
+        sc = self.standardize if isinstance(self.standardize, ScaleShift) else None
+        yi, y = ops.AtomwiseReduceFn.apply(raw, z.contiguous().long() if self.atomref is not None else None,
+                                           self.atomref.weight if self.atomref is not None else None,
+                                           sc.mean.float() if sc is not None else None,
+                                           sc.stddev.float() if sc is not None else None, mol_ptr, int(n_mol), mode)
+        result[self.property] = y
+        if self.contributions:
+            result[self.contributions] = yi
+        if self.derivative:
+            sign = -1.0 if self.negative_dr else 1.0
+            dy = grad(outputs=result[self.property], inputs=[inputs.pos],
+                      grad_outputs=torch.ones_like(result[self.property]), create_graph=self.create_graph,
+                      retain_graph=True)[0]
+            result[self.derivative] = sign * dy
+        return result

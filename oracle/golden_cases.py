@@ -25,6 +25,17 @@ CASES = {
                      atoms=[12, 14], seed=4),
 }
 
+# read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
+# representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
+HEAD_CASES = {
+    # BASELINE configs[2] flags at reduced size: aspirin-shape molecules (21 atoms), lmax=2, yaml flags, SiLU head
+    "head_forces_l2": dict(cfg=OracleConfig(n_atom_basis=64, n_interactions=3, lmax=2, sep_dir=True, sep_tensor=True,
+                                            scale_edge=False), atoms=[21, 21, 7], seed=5, activation="silu"),
+    # class defaults (lmax=1), shifted-softplus head (the reference's Atomwise default activation)
+    "head_forces_ssp": dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=1), atoms=[9, 12], seed=6,
+                            activation="ssp"),
+}
+
 
 def blob(n_atoms, seed, sigma0=1.45):
     """Gaussian-blob molecules of the given sizes: z [N] i64, pos [N,3] f32, batch [N] i64."""

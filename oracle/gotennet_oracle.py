@@ -402,6 +402,73 @@ def wrapper_forward(sd, cfg: OracleConfig, z, pos, batch, intermediates: Optiona
 # --------------------------------------------------------------------------
 # synthetic molecules (SURVEY.md §8d generator)
 # --------------------------------------------------------------------------
+# --------------------------------------------------------------------------
+# read-out head (components/outputs.py:232-376 Atomwise)
+# --------------------------------------------------------------------------
+def head_neurons(n_in: int, n_out: int = 1, n_layers: int = 2, n_hidden=None) -> List[int]:
+    """SchnetMLP layer widths (components/layers.py:241-257): pyramidal halving when n_hidden is None."""
+    if n_hidden is None:
+        c, out = n_in, []
+        for _ in range(n_layers):
+            out.append(c)
+            c = c // 2
+        return out + [n_out]
+    if isinstance(n_hidden, int):
+        n_hidden = [n_hidden] * (n_layers - 1)
+    return [n_in] + list(n_hidden) + [n_out]
+
+
+def make_head_state_dict(n_in: int, n_out: int = 1, n_layers: int = 2, n_hidden=None, seed: int = 0, max_z: int = 100,
+                         atomref: bool = True, dtype=torch.float32) -> Dict[str, Tensor]:
+    """Deterministic weights under the reference's Atomwise key names (probe: `atomref.weight`,
+    `out_net.1.out_net.i.{weight,bias}`, `standardize.{mean,stddev}`)."""
+    g = torch.Generator().manual_seed(10_000 + seed)
+    nn_ = head_neurons(n_in, n_out, n_layers, n_hidden)
+    sd: Dict[str, Tensor] = {}
+    if atomref:
+        sd["atomref.weight"] = torch.randn(max_z, n_out, generator=g, dtype=torch.float64).to(dtype)
+    for i in range(len(nn_) - 1):
+        bound = math.sqrt(6.0 / (nn_[i] + nn_[i + 1]))
+        sd[f"out_net.1.out_net.{i}.weight"] = ((torch.rand(nn_[i + 1], nn_[i], generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        sd[f"out_net.1.out_net.{i}.bias"] = ((torch.rand(nn_[i + 1], generator=g, dtype=torch.float64) * 2 - 1) * 0.1).to(dtype)
+    sd["standardize.mean"] = torch.tensor([0.37], dtype=dtype)
+    sd["standardize.stddev"] = torch.tensor([1.83], dtype=dtype)
+    return sd
+
+
+def atomwise_forward(sd: Dict[str, Tensor], h: Tensor, z: Tensor, batch: Tensor, n_mol: int, activation: str = "silu",
+                     aggregation_mode: Optional[str] = "sum") -> Tuple[Tensor, Tensor]:
+    """Atomwise.forward (outputs.py:323-363): SchnetMLP on the scalar representation (Dense = linear -> act,
+    layers.py:523-528; last layer linear) -> ScaleShift (layers.py:200) -> + atomref[z] (outputs.py:349-351) ->
+    scatter over molecules (outputs.py:354-355).  Returns (y [n_mol, n_out] or yi when mode is None, yi [N, n_out])."""
+    x = h
+    n_lin = len([k for k in sd if k.startswith("out_net.1.out_net.") and k.endswith(".weight")])
+    for i in range(n_lin):
+        x = F.linear(x, sd[f"out_net.1.out_net.{i}.weight"], sd[f"out_net.1.out_net.{i}.bias"])
+        if i < n_lin - 1:
+            x = F.silu(x) if activation == "silu" else F.softplus(x) - math.log(2.0)  # layers.py:81, :619
+    yi = x * sd["standardize.stddev"] + sd["standardize.mean"]
+    if "atomref.weight" in sd:
+        yi = yi + sd["atomref.weight"][z]
+    if aggregation_mode is None:
+        return yi, yi
+    y = torch.zeros(n_mol, yi.shape[1], dtype=yi.dtype).index_add_(0, batch, yi)
+    if aggregation_mode == "mean":
+        y = y / torch.bincount(batch, minlength=n_mol).clamp(min=1).to(yi.dtype).unsqueeze(1)
+    return y, yi
+
+
+def energy_and_forces(sd, sd_head, cfg: OracleConfig, z, pos, batch, n_mol: int, activation: str = "silu"):
+    """Representation + Atomwise(derivative=..., negative_dr=True) (goten_model.py:289, outputs.py:365-375):
+    E [n_mol,1] and F = -dE/dpos [N,3] (differentiable: create_graph=True)."""
+    if not pos.requires_grad:
+        pos = pos.clone().requires_grad_(True)
+    h, X = wrapper_forward(sd, cfg, z, pos, batch)
+    y, yi = atomwise_forward(sd_head, h, z, batch, n_mol, activation)
+    (dy,) = torch.autograd.grad(y, [pos], grad_outputs=torch.ones_like(y), create_graph=True, retain_graph=True)
+    return y, -dy, h
+
+
 def synth_batch(kind: str, n_mol: int, seed: int = 0):
     """Deterministic synthetic batches: returns z [N] int64, pos [N,3] f32, batch [N] int64."""
     g = torch.Generator().manual_seed(seed)

@@ -271,3 +271,91 @@ def test_no_cpu_path(g):
     d.z, d.pos, d.batch = torch.ones(3, dtype=torch.long), torch.randn(3, 3), torch.zeros(3, dtype=torch.long)
     with pytest.raises(g.GotenError):
         m(d)
+
+
+# ------------------------------------------------ read-out head --
+from oracle.golden_cases import HEAD_CASES, probe_vector  # noqa: E402
+
+
+class DataNS:  # PyG-like: attribute and item access
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+
+def build_head(g, cfg, sdh, activation, dev, **kw):
+    import torch.nn.functional as F
+    head = g.Atomwise(n_in=cfg.n_atom_basis, activation=F.silu if activation == "silu" else g.shifted_softplus,
+                      mean=sdh["standardize.mean"].clone(), stddev=sdh["standardize.stddev"].clone(),
+                      atomref=sdh["atomref.weight"].clone(), property="property", contributions="contrib", **kw)
+    head.load_state_dict(sdh, strict=True)
+    return head.to(dev)
+
+
+@pytest.mark.parametrize("name", list(HEAD_CASES))
+def test_head_energy_forces_golden(g, dev, name, golden_dir):
+    """GotenNetWrapper + Atomwise(derivative='forces') against the verbatim reference: energy, forces,
+    contributions, and the gradients of (E*w).sum() for every head / representation parameter."""
+    spec = HEAD_CASES[name]
+    cfg = spec["cfg"]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    n_mol = len(spec["atoms"])
+    rep = build(g, cfg, orc.make_state_dict(cfg, seed=spec["seed"]), dev)
+    head = build_head(g, cfg, orc.make_head_state_dict(cfg.n_atom_basis, seed=spec["seed"]), spec["activation"], dev,
+                      derivative="forces")
+    d = DataNS()
+    d.z, d.pos, d.batch = z.to(dev), pos.to(dev).requires_grad_(True), batch.to(dev)
+    h, X = rep(d)
+    d.representation, d.vector_representation = h, X
+    res = head(d)
+    assert res["property"].shape == (n_mol, 1) and res["forces"].shape == (z.numel(), 3)
+    assert rel(res["property"].detach(), gold["energy"]) < TOL
+    assert rel(res["forces"].detach(), gold["forces"]) < TOL
+    assert rel(res["contrib"].detach(), gold["contrib"]) < TOL
+    w = probe_vector(n_mol).unsqueeze(1).to(dev)
+    ((res["property"] * w).sum()).backward()
+    hp, rp = dict(head.named_parameters()), dict(rep.named_parameters())
+    n = 0
+    for k in gold.files:
+        if k.startswith("gradh_"):
+            assert rel(grad_fingerprint(hp[k[6:]].grad.cpu()), gold[k]) < TOL, k
+            n += 1
+        elif k.startswith("grad_"):
+            p = rp[k[5:]]
+            gr = p.grad if p.grad is not None else torch.zeros_like(p)
+            assert rel(grad_fingerprint(gr.cpu()), gold[k]) < TOL, k
+            n += 1
+    assert n == 4 + len(orc.state_dict_spec(cfg))
+    # back-propagating THROUGH the forces needs second-order kernels: must raise, never silently drop terms
+    d2 = DataNS()
+    d2.z, d2.pos, d2.batch = z.to(dev), pos.to(dev).requires_grad_(True), batch.to(dev)
+    d2.representation, d2.vector_representation = rep(d2)
+    f2 = head(d2)["forces"]
+    with pytest.raises(RuntimeError):
+        f2.pow(2).sum().backward()
+
+
+def test_head_modes_and_batch_checks(g, dev):
+    gen = torch.Generator().manual_seed(0)
+    h = torch.randn(11, 16, generator=gen)
+    z = torch.randint(1, 9, (11,), generator=gen)
+    batch = torch.tensor([0] * 4 + [1] * 1 + [2] * 6)
+    sdh = orc.make_head_state_dict(16, seed=1)
+    cfg = orc.OracleConfig(n_atom_basis=16)
+    for mode in ("sum", "mean", None):
+        head = build_head(g, cfg, sdh, "ssp", dev, aggregation_mode=mode)
+        d = DataNS()
+        d.z, d.batch, d.representation = z.to(dev), batch.to(dev), h.to(dev).requires_grad_(True)
+        out = head(d)
+        yo, yio = orc.atomwise_forward(sdh, h, z, batch, 3, "ssp", mode)
+        assert rel(out["property"], yo) < 1e-5 and rel(out["contrib"], yio) < 1e-5
+        ho = h.clone().requires_grad_(True)
+        yo2, _ = orc.atomwise_forward(sdh, ho, z, batch, 3, "ssp", mode)
+        yo2.pow(2).sum().backward()
+        out["property"].pow(2).sum().backward()
+        assert rel(d.representation.grad, ho.grad) < 1e-5
+    head = build_head(g, cfg, sdh, "ssp", dev)
+    d = DataNS()
+    d.z, d.batch, d.representation = z.to(dev), batch.flip(0).to(dev), h.to(dev)
+    with pytest.raises(g.GotenError):
+        head(d)  # unsorted batch vector

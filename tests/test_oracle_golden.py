@@ -91,3 +91,50 @@ def test_rotation_equivariance_lmax2():
     assert rel(h2, h1) < 1e-9
     assert rel(X2[:, :3], torch.einsum("ab,nbc->nac", q, X1[:, :3])) < 1e-9
     assert rel(X2[:, 3:].pow(2).sum(1), X1[:, 3:].pow(2).sum(1)) < 1e-9
+
+
+# ------------------------------------------------ read-out head --
+from oracle.golden_cases import HEAD_CASES, probe_vector  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(HEAD_CASES))
+def test_oracle_head_matches_reference_golden(name, golden_dir):
+    """Energy, forces (-dE/dpos), per-atom contributions and all parameter gradients of the oracle's
+    Atomwise restatement against the verbatim reference head (tests/golden/make_golden_head.py)."""
+    spec = HEAD_CASES[name]
+    cfg = spec["cfg"]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    n_mol = len(spec["atoms"])
+    sd = {k: v.clone().requires_grad_("radial_basis" not in k) for k, v in orc.make_state_dict(cfg, seed=spec["seed"]).items()}
+    sdh = {k: v.clone().requires_grad_(k.startswith("out_net")) for k, v in
+           orc.make_head_state_dict(cfg.n_atom_basis, seed=spec["seed"]).items()}
+    E, Fo, h = orc.energy_and_forces(sd, sdh, cfg, z, pos, batch, n_mol, spec["activation"])
+    assert rel(E.detach(), gold["energy"]) < TOL and rel(Fo.detach(), gold["forces"]) < TOL
+    _, yi = orc.atomwise_forward(sdh, h, z, batch, n_mol, spec["activation"])
+    assert rel(yi.detach(), gold["contrib"]) < TOL
+    ((E * probe_vector(n_mol).unsqueeze(1)).sum()).backward()
+    n = 0
+    for k in gold.files:
+        if k.startswith("gradh_"):
+            assert rel(grad_fingerprint(sdh[k[6:]].grad), gold[k]) < TOL, k
+            n += 1
+        elif k.startswith("grad_"):
+            g = sd[k[5:]].grad
+            assert rel(grad_fingerprint(g if g is not None else torch.zeros_like(sd[k[5:]])), gold[k]) < TOL, k
+            n += 1
+    assert n == 4 + len(orc.state_dict_spec(cfg))
+
+
+def test_oracle_head_modes():
+    """mean aggregation = sum / atom count; None returns the per-atom values (outputs.py:354-357)."""
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(11, 16, generator=g)
+    z = torch.randint(1, 9, (11,), generator=g)
+    batch = torch.tensor([0] * 4 + [1] * 1 + [2] * 6)
+    sdh = orc.make_head_state_dict(16, seed=1)
+    ys, yi = orc.atomwise_forward(sdh, h, z, batch, 3, "ssp", "sum")
+    ym, _ = orc.atomwise_forward(sdh, h, z, batch, 3, "ssp", "mean")
+    yn, _ = orc.atomwise_forward(sdh, h, z, batch, 3, "ssp", None)
+    assert torch.allclose(ym, ys / torch.tensor([[4.0], [1.0], [6.0]]), atol=1e-6) and torch.equal(yn, yi)
+    assert torch.allclose(ys[1], yi[4], atol=1e-6)
