@@ -66,6 +66,7 @@ class _Lib:
                 "(needs nvcc); gotennet_b200 has no CPU or PyTorch fallback."
             )
         self.path = path
+        self.profile = None
         self.cdll = ctypes.CDLL(path)
         self.protos = parse_header()
         for name, (ret, params) in self.protos.items():
@@ -77,7 +78,15 @@ class _Lib:
             raise GotenError(f"ABI version mismatch: library {ver}, binding 1")
 
     def call(self, name: str, *args):
-        rc = getattr(self.cdll, name)(*args)
+        if self.profile is not None:  # bench.py: CUDA events around every entry point (never on by default)
+            import torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            rc = getattr(self.cdll, name)(*args)
+            e1.record()
+            self.profile.append((name, args, e0, e1))
+        else:
+            rc = getattr(self.cdll, name)(*args)
         if rc != 0:
             raise GotenError(f"{name} failed: {self.cdll.goten_last_error().decode()}")
 
