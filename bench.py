@@ -111,7 +111,7 @@ def kernel_report(prof, n_steps, N, E, peaks, ms_step):
         d = agg.setdefault(name, [0, 0.0])
         d[0] += 1
         d[1] += ms
-        if name == "goten_gemm":
+        if name == "goten_gemm_scaled":
             key = (int(a[8]), int(a[9]), int(a[10]), int(a[2]), int(a[5]))  # M, N, K, trans_a, trans_b
             g = gemm_shapes.setdefault(key, [0, 0.0])
             g[0] += 1
@@ -123,13 +123,13 @@ def kernel_report(prof, n_steps, N, E, peaks, ms_step):
         if name in alg_bytes:
             gbs = alg_bytes[name] * cnt / (ms * 1e-3) / 1e9
             row.update(bound="hbm", achieved_gbs=gbs, frac=gbs / hbm, algorithmic_mb_per_call=alg_bytes[name] / 1e6)
-        elif name == "goten_gemm":
+        elif name == "goten_gemm_scaled":
             fl = sum(2.0 * k[0] * k[1] * k[2] * c for k, (c, _) in gemm_shapes.items())
             row.update(bound="tensor", achieved_tflops=fl / (ms * 1e-3) / 1e12, frac=fl / (ms * 1e-3) / 1e12 / bf16)
         kernels.append(row)
     # dominant kernel: the tcgen05 GEMM; the roofline entry is quoted on its heaviest launch shape
     (M, Nn, K, ta, tb), (cnt, ms) = max(gemm_shapes.items(), key=lambda kv: kv[1][1])
-    g_cnt, g_ms = agg["goten_gemm"]
+    g_cnt, g_ms = agg["goten_gemm_scaled"]
     fl_all = sum(2.0 * k[0] * k[1] * k[2] * c for k, (c, _) in gemm_shapes.items())
     achieved = 2.0 * M * Nn * K * cnt / (ms * 1e-3) / 1e12
     traffic = None
@@ -137,18 +137,29 @@ def kernel_report(prof, n_steps, N, E, peaks, ms_step):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"gemm_{M}x{Nn}x{K}_{ta}{tb}")
     except Exception:
         pass
+    arm16 = os.environ.get("GOTEN_GEMM", "auto") in ("auto", "tc16") and os.environ.get("GOTEN_TC16", "1") != "0"
+    mma_per_product = 3.0 if arm16 else 6.0  # 16-bit MMA slots per fp32-accurate product
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(
+            f"gemm{'16' if arm16 else ''}_{M}x{Nn}x{K}_{ta}{tb}")
+    except Exception:
+        traffic = None
     roofline = {
-        "kernel": f"tc::gemm3x_kernel (tcgen05 3xTF32, CTA pairs) at its heaviest shape M={M} N={Nn} K={K} "
-                  f"trans=({ta},{tb}), {cnt // n_steps} launches/step",
+        "kernel": (f"tc16::gemm16_kernel (tcgen05 split-fp16: hi*hi + hi*lo + lo*hi, CTA pairs)" if arm16 else
+                   f"tc::gemm3x_kernel (tcgen05 3xTF32, CTA pairs)") +
+                  f" at its heaviest shape M={M} N={Nn} K={K} trans=({ta},{tb}), {cnt // n_steps} launches/step",
         "bound": "tensor", "achieved": achieved, "peak": bf16, "unit": "TFLOP/s", "frac": achieved / bf16,
         "traffic": traffic,
         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF",
         "share_of_step": g_ms / n_steps / ms_step, "launches_per_step": g_cnt // n_steps,
         "family_achieved_tflops": fl_all / (g_ms * 1e-3) / 1e12,
-        "note": "fp32-accurate GEMM: three tf32 MMAs per product (hi*hi + hi*lo + lo*hi), each tf32 MMA costs two "
-                "bf16 MMA slots, so the ceiling of this kernel is peak/6; achieved*6/peak is its tensor-pipe fraction "
-                "(ncu: 86-89 % tensor-pipe active at the power-limited 1.5 GHz clock, profiles/)",
-        "tensor_pipe_frac": achieved * 6.0 / bf16,
+        "note": ("fp32-accurate GEMM: operands scaled by a power of two and split x = hi + lo in fp16 (22 significant "
+                 "bits), three kind::f16 MMAs per product with fp32 accumulation, so the ceiling of this kernel is "
+                 "peak/3; achieved*3/peak is its tensor-pipe fraction.  The time is the whole goten_gemm_scaled call "
+                 "(operand max / split passes and split-K reduction included)") if arm16 else
+                ("fp32-accurate GEMM: three tf32 MMAs per product (hi*hi + hi*lo + lo*hi), each tf32 MMA costs two "
+                 "bf16 MMA slots, so the ceiling of this kernel is peak/6; achieved*6/peak is its tensor-pipe fraction"),
+        "tensor_pipe_frac": achieved * mma_per_product / bf16,
     }
     return roofline, kernels
 

@@ -68,6 +68,15 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// Running max |.| of the values a kernel writes into a GEMM operand: the split-fp16 GEMM (gemm_tc16.cu) scales its
+// operands by a power of two derived from this bound.  `out` holds a non-negative float, compared as unsigned bits.
+__device__ __forceinline__ float amax4(float m, float a, float b, float c, float d) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(a), fabsf(b))), fmaxf(fabsf(c), fabsf(d)));
+}
+__device__ __forceinline__ void amax_commit(float* out, float amx) {
+  if (out != nullptr && amx > __ldcg(out)) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(amx));
+}
+
 // degree-l block boundaries inside the L axis: l = 1..lmax occupies [l^2-1, (l+1)^2-1)
 __host__ __device__ __forceinline__ constexpr int blk_lo(int l) { return l * l - 1; }            // l >= 1
 __host__ __device__ __forceinline__ constexpr int blk_hi(int l) { return (l + 1) * (l + 1) - 1; }

@@ -260,8 +260,10 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
                                     const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
                                     const int32_t* __restrict__ src, int N, int C, int H, int max_deg, int g_cols,
                                     float* __restrict__ g_qk, int ldgqk, float* __restrict__ gZe, int ldgz,
-                                    float* __restrict__ da_out, float* __restrict__ g_fc, float* __restrict__ g_Y) {
+                                    float* __restrict__ da_out, float* __restrict__ g_fc, float* __restrict__ g_Y,
+                                    float* __restrict__ gze_amax) {
   using Cf = GataCfg<LMAX, SD, ST>;
+  float amx = 0.f;
   constexpr int L = Cf::L, S = Cf::S;
   extern __shared__ float smem_f[];
   __shared__ float red[33];
@@ -374,6 +376,7 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
       for (int q = 0; q < V; ++q) {
         gq[q] = fmaf(dal * kj[q], siluf_(zre[q]), gq[q]);
         gz[q] = dal * qi[q] * kj[q] * dsiluf_(zre[q]);
+        amx = fmaxf(amx, fabsf(gz[q]));
       }
       stv<V>(gZe + e * ldgz + c, gz);
       float Xj[L][V], y[L], dout[S][V];
@@ -387,7 +390,7 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
         float xv[V], gtf[V];
         ldv<V>(x + (size_t)j * SC + col, xv);
 #pragma unroll
-        for (int q = 0; q < V; ++q) gtf[q] = dout[k][q] * xv[q] * f;
+        for (int q = 0; q < V; ++q) { gtf[q] = dout[k][q] * xv[q] * f; amx = fmaxf(amx, fabsf(gtf[q])); }
         stv<V>(gZe + e * ldgz + C + col, gtf);
         if (geom) {
           float tf[V], vv[V];
@@ -425,6 +428,7 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
     }
   }
   if (act) stv<V>(g_qk + (size_t)i * ldgqk + c, gq);
+  amax_commit(gze_amax, amx);
 }
 
 // --------------------------------------------------------- backward, source ---
@@ -575,7 +579,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                         const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax,
                         int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe, int ldgz, float* da,
-                        cudaStream_t st, bool* handled);
+                        float* gze_amax, cudaStream_t st, bool* handled);
 int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                         const float* alpha, const float* da, const int32_t* src_ptr, const int32_t* src_perm,
@@ -661,7 +665,7 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
                        const float* x, const float* v, const float* Ze, int ldz, const float* Y, const float* fc,
                        const float* kappa, const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N,
                        int C, int H, int lmax, int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe,
-                       int ldgz, float* da, float* g_fc, float* g_Y, void* stream) {
+                       int ldgz, float* da, float* g_fc, float* g_Y, float* gze_amax, void* stream) {
   const int V = (gata_vec(C, H, ldqk, ldz) == 4 && ldgqk % 4 == 0 && ldgz % 4 == 0) ? 4 : 1;
   if (gata_check(C, H, lmax, V)) return 1;
   if (N == 0) return 0;
@@ -669,7 +673,7 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
   if (use_staged() && g_fc == nullptr && g_Y == nullptr) {  // geometry gradients (forces) stay on the kernels below
     bool handled = false;
     if (gata_bwd_tgt_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H, lmax,
-                            flags, max_deg_in, g_qk, ldgqk, gZe, ldgz, da, st, &handled))
+                            flags, max_deg_in, g_qk, ldgqk, gZe, ldgz, da, gze_amax, st, &handled))
       return 1;
     if (handled) return 0;
   }
@@ -681,7 +685,7 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
   const size_t smem = gata_smem_floats(max_deg_in, nparts, H, L, true) * sizeof(float);
   GOTEN_REQUIRE(smem <= 200 * 1024, "max in-degree %d needs %zu B of shared memory", max_deg_in, smem);
   GATA_DISPATCH(gata_bwd_tgt_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr,
-                src, N, C, H, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, g_fc, g_Y);
+                src, N, C, H, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, g_fc, g_Y, gze_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

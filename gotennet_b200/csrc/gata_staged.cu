@@ -229,8 +229,9 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
                                            const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
                                            const int32_t* __restrict__ src, int N, int C, int H, int R, int max_deg,
                                            int g_cols, float* __restrict__ g_qk, int ldgqk, float* __restrict__ gZe,
-                                           int ldgz, float* __restrict__ da_out) {
+                                           int ldgz, float* __restrict__ da_out, float* __restrict__ gze_amax) {
   using Cf = Cfg<LMAX, SD, ST>;
+  float amx = 0.f;
   constexpr int L = Cf::L, S = Cf::S, ND = Cf::ND;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, c = tid * 4, C4 = C >> 2;
@@ -319,7 +320,9 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
         for (int k = 0; k < S; ++k) {
           const float4 vv = st[(L + k) * C4 + tid], xv = st[(L + S + k) * C4 + tid];
           pk[k] = dout[k].x * vv.x + dout[k].y * vv.y + dout[k].z * vv.z + dout[k].w * vv.w;
-          st4(gz + k * C, make_float4(dout[k].x * xv.x * f, dout[k].y * xv.y * f, dout[k].z * xv.z * f, dout[k].w * xv.w * f));
+          const float4 gv = make_float4(dout[k].x * xv.x * f, dout[k].y * xv.y * f, dout[k].z * xv.z * f, dout[k].w * xv.w * f);
+          amx = amax4(amx, gv.x, gv.y, gv.z, gv.w);
+          st4(gz + k * C, gv);
         }
       }
 #pragma unroll
@@ -382,13 +385,15 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
         gq.y = fmaf(dal * kj[u].y, siluf_(zr[u].y), gq.y);
         gq.z = fmaf(dal * kj[u].z, siluf_(zr[u].z), gq.z);
         gq.w = fmaf(dal * kj[u].w, siluf_(zr[u].w), gq.w);
-        st4(gZe + (size_t)(e0 + t0 + u) * ldgz + c,
-            make_float4(dal * qi.x * kj[u].x * dsiluf_(zr[u].x), dal * qi.y * kj[u].y * dsiluf_(zr[u].y),
-                        dal * qi.z * kj[u].z * dsiluf_(zr[u].z), dal * qi.w * kj[u].w * dsiluf_(zr[u].w)));
+        const float4 gv = make_float4(dal * qi.x * kj[u].x * dsiluf_(zr[u].x), dal * qi.y * kj[u].y * dsiluf_(zr[u].y),
+                                      dal * qi.z * kj[u].z * dsiluf_(zr[u].z), dal * qi.w * kj[u].w * dsiluf_(zr[u].w));
+        amx = amax4(amx, gv.x, gv.y, gv.z, gv.w);
+        st4(gZe + (size_t)(e0 + t0 + u) * ldgz + c, gv);
       }
     }
   }
   st4(g_qk + (size_t)i * ldgqk + c, gq);
+  amax_commit(gze_amax, amx);
 }
 
 // --------------------------------------------------------- backward, source ---
@@ -637,7 +642,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                         const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax,
                         int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe, int ldgz, float* da,
-                        cudaStream_t st, bool* handled) {
+                        float* gze_amax, cudaStream_t st, bool* handled) {
   *handled = false;
   const int D = C / H;
   if (C % 4 != 0 || D % 4 != 0 || ldqk % 4 != 0 || ldz % 4 != 0 || ldgqk % 4 != 0 || ldgz % 4 != 0) return 0;
@@ -659,7 +664,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   const size_t smem = R * stage_bytes + tail;
   if (R * stage_bytes + tail > 220 * 1024) return 0;
   STAGED_DISPATCH(gata_bwd_tgt_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha,
-                  tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da);
+                  tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
   return 0;

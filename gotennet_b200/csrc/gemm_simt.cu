@@ -340,6 +340,11 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
             int N, int K, const float* bias, const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo,
               int act_hi, float* colsum,
             void* workspace, int64_t workspace_bytes, cudaStream_t st, bool* handled);
+int64_t gemm_tc16_workspace_bytes(int M, int N, int K, int trans_a, int trans_b);
+int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc, int M, int N,
+              int K, const float* bias, const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo,
+              int act_hi, float* colsum, const float* a_amax, const float* b_amax, void* workspace,
+              int64_t workspace_bytes, cudaStream_t st, bool* handled);
 int64_t gemm_tc_workspace_bytes(int M, int N, int K, int trans_a, int trans_b);
 }  // namespace goten
 
@@ -348,14 +353,29 @@ extern "C" {
 int64_t goten_gemm_workspace_bytes(int M, int N, int K, int trans_a, int trans_b) {
   int64_t a = gemm_simt_workspace_bytes(M, N, K, trans_a);
   int64_t b = gemm_tc_workspace_bytes(M, N, K, trans_a, trans_b);
-  return a > b ? a : b;
+  int64_t c = gemm_tc16_workspace_bytes(M, N, K, trans_a, trans_b);
+  a = a > b ? a : b;
+  return a > c ? a : c;
 }
 
-int goten_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc, int M,
-               int N, int K, const float* bias, const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo,
-              int act_hi, float* colsum,
-               void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+// impl: 0 = auto (split-fp16 tcgen05 -> 3xTF32 tcgen05 -> fp32 SIMT, first arm that accepts the shape),
+//       1 = fp32 SIMT, 2 = 3xTF32 tcgen05, 3 = split-fp16 tcgen05.  GOTEN_TC16=0 removes the fp16 arm from auto.
+int goten_gemm_scaled(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc,
+                      int M, int N, int K, const float* bias, const float* add_src, int ld_add, float* act_out,
+                      int ld_act, int act_lo, int act_hi, float* colsum, const float* a_amax, const float* b_amax,
+                      void* workspace, int64_t workspace_bytes, int impl, void* stream) {
   cudaStream_t st = as_stream(stream);
+  static int auto16 = -1;
+  if (auto16 < 0) { const char* e = getenv("GOTEN_TC16"); auto16 = e ? atoi(e) : 1; }
+  if (impl == 3 || (impl == 0 && auto16)) {
+    bool handled = false;
+    int rc = gemm_tc16(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, add_src, ld_add, act_out, ld_act,
+                       act_lo, act_hi, colsum, a_amax, b_amax, workspace, workspace_bytes, st, &handled);
+    if (rc) return rc;
+    if (handled) return 0;
+    GOTEN_REQUIRE(impl == 0, "tcgen05 fp16 GEMM does not support this shape/layout (M=%d N=%d K=%d ta=%d tb=%d)", M, N,
+                  K, trans_a, trans_b);
+  }
   if (impl == 0 || impl == 2) {
     bool handled = false;
     int rc = gemm_tc(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, add_src, ld_add, act_out, ld_act, act_lo,
@@ -367,6 +387,13 @@ int goten_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, in
   }
   return gemm_simt(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, add_src, ld_add, act_out, ld_act, act_lo,
                    act_hi, colsum, workspace, workspace_bytes, st);
+}
+
+int goten_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc, int M,
+               int N, int K, const float* bias, const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo,
+               int act_hi, float* colsum, void* workspace, int64_t workspace_bytes, int impl, void* stream) {
+  return goten_gemm_scaled(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, add_src, ld_add, act_out, ld_act,
+                           act_lo, act_hi, colsum, nullptr, nullptr, workspace, workspace_bytes, impl, stream);
 }
 
 int goten_dsilu_mul(const float* g, int ldg, const float* pre, int ldp, float* out, int ldo, int64_t M, int N,

@@ -1,0 +1,737 @@
+// tcgen05 split-fp16 GEMM for sm_100a: fp32-accurate tensor-core GEMM at the 16-bit MMA rate
+//     x' = x * 2^s (per-tensor power-of-two scale from the tensor's max |x|, so max |x'| is in [2^14, 2^15))
+//     x_hi = fp16(x'),  x_lo = fp16(x' - x_hi)          (22 significant bits; the absolute error floor of the
+//                                                        fp16 subnormals is 2^-40 of the tensor maximum)
+//     D = (A_lo B_hi + A_hi B_lo + A_hi B_hi) * 2^-(sA+sB)        three kind::f16 MMAs, fp32 accumulation in TMEM
+// (the reference runs its nn.Linear layers in strict fp32, scripts/train.py:16; three tf32 MMAs - gemm_tc.cu - cost
+//  two 16-bit MMA slots each, this form costs one each: same accuracy class at twice the tensor-pipe throughput).
+//
+// Structure (persistent, warp specialised, one CTA per SM, 320 threads) as in gemm_tc.cu:
+//   warp 0      TMA producer: raw fp32 A tile + pre-split fp16 B_hi / B_lo tiles -> smem ring
+//   warp 1      TMEM allocator + MMA issuer: 12 x tcgen05.mma.kind::f16 (M128/256 x N<=256 x K16) per 64-deep k-block
+//   warps 2-5   epilogue: tcgen05.ld -> un-scale -> smem -> TMA store / fused bias + residual + SiLU side output
+//   warps 6-9   converter: scales and splits the raw A tile IN PLACE into K-major 128B-swizzled fp16 hi / lo tiles.
+//               For the weight-gradient GEMM (A given as [R][M], reduction over rows) the converter also transposes,
+//               so every MMA of this file uses the plain K-major SWIZZLE_128B operand layout.
+// B is always staged K-major: the pre-split kernels write fp16 hi / lo copies [N][K] (transposing when B is [K][N]).
+#include <cuda_fp16.h>
+
+#include "umma.cuh"
+
+namespace goten {
+
+namespace tc16 {
+
+using namespace tc;
+
+constexpr int BM = 128;          // UMMA M per CTA (cta_group::2: the pair computes M = 256)
+constexpr int BK = 64;           // halves per k-block = one 128 B swizzle row
+constexpr int MAX_STAGES = 4;
+constexpr int NTHREADS = 320;
+constexpr int EPI_WARP0 = 2, CONV_WARP0 = 6;
+constexpr uint32_t A_BYTES = BM * BK * 4;   // raw fp32 tile = hi + lo fp16 tiles = 32 KB
+
+// power-of-two scale that maps a tensor maximum into [2^14, 2^15), and its inverse (both exact floats)
+__device__ __forceinline__ float scale_of(float amax) {
+  const int e = (int)((__float_as_uint(amax) >> 23) & 0xFF);
+  if (amax == 0.f || e == 255) return 1.0f;
+  int sb = 268 - e;  // biased exponent of 2^(14 - (e - 127))
+  sb = sb < 1 ? 1 : (sb > 253 ? 253 : sb);
+  return __uint_as_float((uint32_t)sb << 23);
+}
+__device__ __forceinline__ float inv_scale_of(float amax) {
+  const float s = scale_of(amax);
+  return __uint_as_float((uint32_t)(254 - (int)(__float_as_uint(s) >> 23)) << 23);
+}
+
+// hi/lo split of two scaled values -> packed half2 words
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+struct Params {
+  int M, N, K;
+  int block_n;
+  int n_mt, n_nt;
+  int splits, kb_per_split, kb_total;
+  int stages;
+  float* C; int ldc;
+  const float* bias;
+  const float* add_src; int ld_add;
+  float* act_out; int ld_act, act_lo, act_hi;
+  int add_vec, c_vec;
+  float* partial;
+  float* colsum;
+  float* partial_colsum;
+  const float* amax;      // [0] = max |A|, [1] = max |B| (device)
+};
+
+template <bool A_ROWS_ARE_K, int NCTA>
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+              const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int BN = p.block_n;
+  const int BNH = BN / NCTA;
+  const int STAGES = p.stages;
+  const uint32_t B_BYTES = (uint32_t)BNH * BK * 2;   // one fp16 B tile (hi or lo), <= 32 KB
+  const uint32_t STAGE_BYTES = A_BYTES + 2 * B_BYTES;
+  uint8_t* epi_smem = smem + STAGES * STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * 2 * 4096);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * MAX_STAGES + 4);
+  const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + MAX_STAGES), bar_empty = smem_u32(bars + 2 * MAX_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 3 * MAX_STAGES), bar_tempty = smem_u32(bars + 3 * MAX_STAGES + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
+  const int unit = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int n_units = NCTA == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_conv + 8 * s, 4 * NCTA);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4 * NCTA);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    if (NCTA == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+  }
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_tiles = p.n_mt * p.n_nt;
+  const int n_items = n_tiles * p.splits;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = unit; w < n_items; w += n_units) {
+        const int split = w / n_tiles, tile = w % n_tiles;
+        const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN + (int)rank * BNH;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(bar_empty + 8 * s, ph ^ 1);
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sbh = sa + A_BYTES, sbl = sbh + B_BYTES;
+          const uint32_t bar = bar_full + 8 * s;
+          mbar_arrive_expect_tx(bar, A_BYTES + 2 * B_BYTES);
+          if (!A_ROWS_ARE_K) {
+            // A[M][K]: two 128B-swizzled boxes of [128 rows][32 floats]
+            tma_load_2d(sa, &tmA, bar, kb * BK, m0);
+            tma_load_2d(sa + A_BYTES / 2, &tmA, bar, kb * BK + 32, m0);
+          } else {
+            // A[R][M]: one un-swizzled box of [64 k rows][128 floats]
+            tma_load_2d(sa, &tmA, bar, m0, kb * BK);
+          }
+          tma_load_2d(sbh, &tmBh, bar, kb * BK, n0);
+          tma_load_2d(sbl, &tmBl, bar, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    if (lane == 0 && rank == 0) {
+      // c = f32 (bit 4), a = b = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * NCTA) >> 4) << 24);
+      uint32_t it = 0, tile_it = 0;
+      for (int w = unit; w < n_items; w += n_units, ++tile_it) {
+        const int split = w / n_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
+        mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+          mbar_wait(bar_full + 8 * s, ph);
+          mbar_wait(bar_conv + 8 * s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+          const uint32_t sal = sa + A_BYTES / 2, sbh = sa + A_BYTES, sbl = sbh + B_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t a_hi = make_desc(sa + kk * 32, 16, 1024, 2), a_lo = make_desc(sal + kk * 32, 16, 1024, 2);
+            const uint64_t b_hi = make_desc(sbh + kk * 32, 16, 1024, 2), b_lo = make_desc(sbl + kk * 32, 16, 1024, 2);
+            if (NCTA == 2) {
+              umma_f16_2cta(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma_f16_2cta(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_f16_2cta(d_tmem, a_hi, b_hi, idesc, 1u);
+            } else {
+              umma_f16(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma_f16(d_tmem, a_hi, b_lo, idesc, 1u);
+              umma_f16(d_tmem, a_hi, b_hi, idesc, 1u);
+            }
+          }
+          if (NCTA == 2) umma_commit_2cta(bar_empty + 8 * s); else umma_commit(bar_empty + 8 * s);
+        }
+        if (NCTA == 2) umma_commit_2cta(bar_tfull + 8 * acc); else umma_commit(bar_tfull + 8 * acc);
+      }
+    }
+  } else if (warp >= CONV_WARP0) {
+    // =============================== converter ==================================
+    const int ct = threadIdx.x - CONV_WARP0 * 32;  // 0..127 = tile row (M index) this thread produces
+    const float sA = scale_of(p.amax[0]);
+    const uint32_t sw = (uint32_t)(ct & 7);
+    uint32_t it = 0;
+    for (int w = unit; w < n_items; w += n_units) {
+      const int split = w / n_tiles, tile = w % n_tiles;
+      const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM;
+      const bool do_cs = A_ROWS_ARE_K && (p.colsum != nullptr) && (tile % p.n_nt == 0);
+      const int kb0 = split * p.kb_per_split;
+      const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+      float csum = 0.f;
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
+        mbar_wait(bar_full + 8 * s, ph);
+        uint8_t* a_raw = smem + s * STAGE_BYTES;
+        uint8_t* hi_row = a_raw + ct * 128;
+        uint8_t* lo_row = hi_row + A_BYTES / 2;
+        if (!A_ROWS_ARE_K) {
+          // thread = tile row: its 64 floats live in row ct of the two raw boxes and are replaced by row ct of the
+          // hi tile (first box) and of the lo tile (second box).  All loads are issued before the first store.
+          float4 v[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c)
+            v[c] = *reinterpret_cast<const float4*>(a_raw + (c >> 3) * (A_BYTES / 2) + ct * 128 + ((((uint32_t)c & 7) ^ sw) << 4));
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {  // 16 B chunk of 8 halves = floats 8c .. 8c+7
+            uint4 h, l;
+            split2(v[2 * c].x * sA, v[2 * c].y * sA, h.x, l.x);
+            split2(v[2 * c].z * sA, v[2 * c].w * sA, h.y, l.y);
+            split2(v[2 * c + 1].x * sA, v[2 * c + 1].y * sA, h.z, l.z);
+            split2(v[2 * c + 1].z * sA, v[2 * c + 1].w * sA, h.w, l.w);
+            const uint32_t off = (((uint32_t)c ^ sw) << 4);
+            *reinterpret_cast<uint4*>(hi_row + off) = h;
+            *reinterpret_cast<uint4*>(lo_row + off) = l;
+          }
+        } else {
+          // thread = MN column ct of the raw [64 k][128 mn] tile: read the column, then (after every converter
+          // thread has read) write it as K-major row ct of the hi / lo tiles
+          float v[BK];
+#pragma unroll
+          for (int k = 0; k < BK; ++k) v[k] = *reinterpret_cast<const float*>(a_raw + k * 512 + ct * 4);
+          conv_bar_sync();
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            uint4 h, l;
+            split2(v[8 * c + 0] * sA, v[8 * c + 1] * sA, h.x, l.x);
+            split2(v[8 * c + 2] * sA, v[8 * c + 3] * sA, h.y, l.y);
+            split2(v[8 * c + 4] * sA, v[8 * c + 5] * sA, h.z, l.z);
+            split2(v[8 * c + 6] * sA, v[8 * c + 7] * sA, h.w, l.w);
+            const uint32_t off = (((uint32_t)c ^ sw) << 4);
+            *reinterpret_cast<uint4*>(hi_row + off) = h;
+            *reinterpret_cast<uint4*>(lo_row + off) = l;
+          }
+          if (do_cs) {
+#pragma unroll
+            for (int k = 0; k < BK; ++k) csum += v[k];
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (NCTA == 2) mbar_arrive_cluster(bar_conv + 8 * s, 0);
+          else mbar_arrive(bar_conv + 8 * s);
+        }
+      }
+      if (do_cs) {
+        const int m = m0 + ct;
+        if (m < p.M) {
+          if (p.partial_colsum) p.partial_colsum[(size_t)split * p.M + m] = csum;
+          else p.colsum[m] = csum;
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue ===================================
+    const int q = warp & 3;
+    uint8_t* my_buf = epi_smem + (warp - EPI_WARP0) * 2 * 4096;
+    const bool fast = (p.add_src == nullptr) && (p.act_out == nullptr);
+    const float un_a = inv_scale_of(p.amax[0]), un_b = inv_scale_of(p.amax[1]);
+    uint32_t tile_it = 0, n_store = 0;
+    for (int w = unit; w < n_items; w += n_units, ++tile_it) {
+      const int split = w / n_tiles, tile = w % n_tiles;
+      const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN;
+      const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
+      mbar_wait(bar_tfull + 8 * acc, aph);
+      tc_fence_after();
+      const int row_base = m0 + q * 32;
+      const bool rows_live = row_base < p.M;
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        const int nc0 = n0 + ch * 32;
+        if (nc0 >= p.N) break;
+        const uint32_t taddr = tmem_base + acc * (uint32_t)BN + ch * 32 + ((uint32_t)(q * 32) << 16);
+        uint32_t r[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (!rows_live) continue;
+        float bl = 0.f;
+        if (p.bias && !p.partial && nc0 + lane < p.N) bl = p.bias[nc0 + lane];
+        uint8_t* buf = my_buf + (n_store & 1) * 4096;
+        if (fast && n_store >= 2) {
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 v;
+          v.x = __uint_as_float(r[4 * c + 0]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 0);
+          v.y = __uint_as_float(r[4 * c + 1]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 1);
+          v.z = __uint_as_float(r[4 * c + 2]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 2);
+          v.w = __uint_as_float(r[4 * c + 3]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 3);
+          *reinterpret_cast<float4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
+        }
+        if (fast) {
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.partial) tma_store_2d(&tmC, smem_u32(buf), nc0, split * p.M + row_base);
+            else tma_store_2d(&tmC, smem_u32(buf), nc0, row_base);
+            bulk_commit();
+          }
+          ++n_store;
+        } else {
+          __syncwarp();
+          const int cq = lane & 7, rsub = lane >> 3;
+          const int n = nc0 + cq * 4;
+          const bool vec_ok = (n + 3 < p.N);
+          float4 addv[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub, m = row_base + rr;
+            addv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.add_src && m < p.M) {
+              const float* ap = p.add_src + (size_t)m * p.ld_add + n;
+              if (vec_ok && p.add_vec) addv[i] = *reinterpret_cast<const float4*>(ap);
+              else {
+                if (n + 0 < p.N) addv[i].x = ap[0];
+                if (n + 1 < p.N) addv[i].y = ap[1];
+                if (n + 2 < p.N) addv[i].z = ap[2];
+                if (n + 3 < p.N) addv[i].w = ap[3];
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub, m = row_base + rr;
+            float4 v = *reinterpret_cast<const float4*>(buf + rr * 128 + ((cq ^ (rr & 7)) << 4));
+            v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
+            if (m < p.M) {
+              float* cp = p.C + (size_t)m * p.ldc + n;
+              if (vec_ok && p.c_vec) *reinterpret_cast<float4*>(cp) = v;
+              else {
+                if (n + 0 < p.N) cp[0] = v.x;
+                if (n + 1 < p.N) cp[1] = v.y;
+                if (n + 2 < p.N) cp[2] = v.z;
+                if (n + 3 < p.N) cp[3] = v.w;
+              }
+              if (p.act_out) {
+                const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int qd = 0; qd < 4; ++qd) {
+                  const int nn = n + qd;
+                  if (nn < p.N && nn >= p.act_lo && nn < p.act_hi)
+                    p.act_out[(size_t)m * p.ld_act + (nn - p.act_lo)] = vv[qd] / (1.0f + __expf(-vv[qd]));
+                }
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
+    }
+    if (fast && lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
+// ---------------------------------------------------------------- operand preparation
+// max |x| over a [rows][cols] matrix with leading dimension ld -> atomicMax on the (non-negative) float bits
+__global__ void absmax_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols, int vec, float* __restrict__ out) {
+  float m = 0.f;
+  if (vec) {
+    const int c4 = cols >> 2;
+    const int64_t total = rows * c4;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / c4;
+      const int c = (int)(idx - r * c4);
+      const float4 v = *reinterpret_cast<const float4*>(in + r * ld + 4 * c);
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    }
+  } else {
+    const int64_t total = rows * cols;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = idx / cols;
+      m = fmaxf(m, fabsf(in[r * ld + (idx - r * cols)]));
+    }
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+}
+
+// B[N][K] (ld) -> fp16 hi / lo [N][Kp]: thread = 4 consecutive k
+__global__ void split16_rows_kernel(const float* __restrict__ in, int ld, int rows, int cols, int Kp, int vec,
+                                    const float* __restrict__ amax, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float s = scale_of(*amax);
+  const int c4 = (cols + 3) >> 2;
+  const int64_t total = (int64_t)rows * c4;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / c4), c = 4 * (int)(idx - (int64_t)r * c4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* ip = in + (int64_t)r * ld + c;
+    if (vec && c + 3 < cols) v = *reinterpret_cast<const float4*>(ip);
+    else {
+      if (c + 0 < cols) v.x = ip[0];
+      if (c + 1 < cols) v.y = ip[1];
+      if (c + 2 < cols) v.z = ip[2];
+      if (c + 3 < cols) v.w = ip[3];
+    }
+    uint2 h, l;
+    split2(v.x * s, v.y * s, h.x, l.x);
+    split2(v.z * s, v.w * s, h.y, l.y);
+    *reinterpret_cast<uint2*>(hi + (int64_t)r * Kp + c) = h;   // Kp % 8 == 0 and c % 4 == 0: 8 B aligned, inside the row
+    *reinterpret_cast<uint2*>(lo + (int64_t)r * Kp + c) = l;
+  }
+}
+
+// B[K][N] (ld) -> fp16 hi / lo [N][Kp] through a 64 x 64 shared-memory tile (coalesced on both sides)
+__global__ void __launch_bounds__(256)
+split16_transpose_kernel(const float* __restrict__ in, int ld, int rows /*K*/, int cols /*N*/, int Kp,
+                         const float* __restrict__ amax, __half* __restrict__ hi, __half* __restrict__ lo) {
+  __shared__ float tile[64][65];
+  const float s = scale_of(*amax);
+  const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;  // 64 x 4
+  for (int y = ty; y < 64; y += 4) {
+    const int r = r0 + y, c = c0 + tx;
+    tile[y][tx] = (r < rows && c < cols) ? in[(int64_t)r * ld + c] * s : 0.f;
+  }
+  __syncthreads();
+  // thread -> (output row c = c0 + oc, 8 consecutive k = r0 + 8 j ..)
+  const int j = threadIdx.x & 7;
+  for (int oc = threadIdx.x >> 3; oc < 64; oc += 32) {
+    const int c = c0 + oc, r = r0 + 8 * j;
+    if (c >= cols || r >= Kp) continue;
+    uint4 h, l;
+    split2(tile[8 * j + 0][oc], tile[8 * j + 1][oc], h.x, l.x);
+    split2(tile[8 * j + 2][oc], tile[8 * j + 3][oc], h.y, l.y);
+    split2(tile[8 * j + 4][oc], tile[8 * j + 5][oc], h.z, l.z);
+    split2(tile[8 * j + 6][oc], tile[8 * j + 7][oc], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + (int64_t)c * Kp + r) = h;   // r % 8 == 0, Kp % 8 == 0: 16 B aligned, inside the row
+    *reinterpret_cast<uint4*>(lo + (int64_t)c * Kp + r) = l;
+  }
+}
+
+}  // namespace tc16
+
+int splitk_finish(const float* partial, const float* partial_cs, int splits, float* C, int ldc, int M, int N,
+                  const float* bias, const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo, int act_hi,
+                  float* colsum, cudaStream_t st);
+
+// 2-D fp32 map over P[rows][cols] (ld floats)
+static bool make_map_f32(CUtensorMap* m, const float* P, int64_t ld, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                         CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(P), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// K-major fp16 operand P[rows][k] (ld halves): box = 64 k x box_rows rows, 128B swizzle
+static bool make_map_f16(CUtensorMap* m, const __half* P, int64_t ld, int64_t rows, int64_t k, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)k, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t es[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(P), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct Tc16Plan {
+  bool ok;
+  bool a_rows_are_k;     // weight-gradient form: A given as [R][M]
+  int block_n, n_mt, n_nt, splits, kb_total, kb_per_split;
+  int ncta, stages;
+  int64_t kp;            // padded K of the pre-split B copies (multiple of 8 halves = 16 B)
+  int64_t b_bytes;       // bytes of each pre-split B copy
+  int64_t ws_bytes;
+};
+
+static Tc16Plan tc16_plan(int M, int N, int K, int trans_a, int trans_b) {
+  Tc16Plan t{};
+  t.ok = false;
+  if (M <= 0 || N <= 0 || K <= 0) return t;
+  if (trans_a && trans_b) return t;
+  if (N < 16) return t;
+  t.a_rows_are_k = trans_a != 0;
+  if (t.a_rows_are_k && M % 32 != 0) return t;  // split-K partial stores are whole 32-row blocks
+  t.block_n = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  static int force_ncta = -1;
+  if (force_ncta < 0) { const char* e = getenv("GOTEN_GEMM_NCTA"); force_ncta = e ? atoi(e) : 0; }
+  t.ncta = (force_ncta == 1) ? 1 : ((M >= 256 || force_ncta == 2) ? 2 : 1);
+  const size_t stage_bytes = tc16::A_BYTES + 2 * (size_t)(t.block_n / t.ncta) * tc16::BK * 2;
+  t.stages = (int)((232448 - 4 * 2 * 4096 - 1024 - 256) / stage_bytes);
+  if (t.stages > tc16::MAX_STAGES) t.stages = tc16::MAX_STAGES;
+  t.n_mt = (M + tc16::BM * t.ncta - 1) / (tc16::BM * t.ncta);
+  t.n_nt = (N + t.block_n - 1) / t.block_n;
+  t.kb_total = (K + tc16::BK - 1) / tc16::BK;
+  t.splits = 1;
+  if (t.a_rows_are_k) {
+    // chains of accumulating MMAs are kept short (see gemm_tc.cu: the tensor core accumulates with truncation);
+    // the fp32 partials are summed with round-to-nearest by the split-K reduction kernel
+    constexpr int MAX_CHAIN_KB = 48;
+    const int tiles = t.n_mt * t.n_nt;
+    int want = (148 / t.ncta) / tiles;
+    if (want < 1) want = 1;
+    int per = (t.kb_total + want - 1) / want;
+    if (per > MAX_CHAIN_KB) per = MAX_CHAIN_KB;
+    if (per < 4) per = t.kb_total < 4 ? t.kb_total : 4;
+    t.splits = (t.kb_total + per - 1) / per;
+  }
+  t.kb_per_split = (t.kb_total + t.splits - 1) / t.splits;
+  t.splits = (t.kb_total + t.kb_per_split - 1) / t.kb_per_split;
+  t.kp = ((int64_t)K + 7) & ~int64_t(7);
+  t.b_bytes = align256((int64_t)N * t.kp * 2);
+  t.ws_bytes = 256 + 2 * t.b_bytes;
+  if (t.splits > 1) t.ws_bytes += align256((int64_t)t.splits * ((int64_t)M * N + M) * 4);
+  t.ok = true;
+  return t;
+}
+
+int64_t gemm_tc16_workspace_bytes(int M, int N, int K, int trans_a, int trans_b) {
+  Tc16Plan t = tc16_plan(M, N, K, trans_a, trans_b);
+  return t.ok ? t.ws_bytes : 0;
+}
+
+static int launch_absmax(const float* P, int64_t ld, int64_t rows, int cols, float* slot, int sm_count, cudaStream_t st) {
+  const int vec = (cols % 4 == 0 && ld % 4 == 0 && aligned16(P)) ? 1 : 0;
+  const int64_t work = vec ? rows * (cols / 4) : rows * cols;
+  int64_t grid = cdiv64(work, 256 * 4);
+  if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+  if (grid < 1) grid = 1;
+  tc16::absmax_kernel<<<(unsigned)grid, 256, 0, st>>>(P, ld, rows, cols, vec, slot);
+  GOTEN_CHECK_LAUNCH();
+  return 0;
+}
+
+// a_amax / b_amax: optional device pointers to a known upper bound of max|A| / max|B| (any bound within a few
+// powers of two of the true maximum keeps full accuracy); nullptr = computed here with one read pass.
+int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b, float* C, int ldc, int M, int N,
+              int K, const float* bias, const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo,
+              int act_hi, float* colsum, const float* a_amax, const float* b_amax, void* workspace,
+              int64_t workspace_bytes, cudaStream_t st, bool* handled) {
+  *handled = false;
+  Tc16Plan t = tc16_plan(M, N, K, trans_a, trans_b);
+  if (!t.ok || workspace == nullptr || workspace_bytes < t.ws_bytes) return 0;
+  if (!aligned16(A) || lda % 4 != 0) return 0;
+  if (colsum && !t.a_rows_are_k) return 0;
+  if (get_encode() == nullptr) return 0;
+  static int sm_count = 0, smem_optin = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    GOTEN_CHECK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    GOTEN_CHECK_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) return 0;
+    sm_count = prop.multiProcessorCount;
+    smem_optin = (int)prop.sharedMemPerBlockOptin;
+  }
+
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  float* amax = reinterpret_cast<float*>(ws);          // [0] A, [1] B
+  __half* Bh = reinterpret_cast<__half*>(ws + 256);
+  __half* Bl = reinterpret_cast<__half*>(ws + 256 + t.b_bytes);
+  float* partial = nullptr;
+  float* partial_cs = nullptr;
+  if (t.splits > 1) {
+    partial = reinterpret_cast<float*>(ws + 256 + 2 * t.b_bytes);
+    partial_cs = partial + (size_t)t.splits * M * N;
+  }
+
+  // ---- scales
+  if (a_amax && b_amax) {
+    GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax, a_amax, 4, cudaMemcpyDeviceToDevice, st));
+    GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax + 1, b_amax, 4, cudaMemcpyDeviceToDevice, st));
+  } else {
+    GOTEN_CHECK_CUDA(cudaMemsetAsync(amax, 0, 8, st));
+    if (a_amax) GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax, a_amax, 4, cudaMemcpyDeviceToDevice, st));
+    else if (launch_absmax(A, lda, t.a_rows_are_k ? K : M, t.a_rows_are_k ? M : K, amax, sm_count, st)) return 1;
+    if (b_amax) GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax + 1, b_amax, 4, cudaMemcpyDeviceToDevice, st));
+    else {
+      const bool b_is_nk = !t.a_rows_are_k && trans_b;   // B[N][K]; otherwise B[K][N]
+      if (launch_absmax(B, ldb, b_is_nk ? N : K, b_is_nk ? K : N, amax + 1, sm_count, st)) return 1;
+    }
+  }
+
+  // ---- B operand: scaled fp16 hi / lo copies, K-major [N][Kp]
+  if (!t.a_rows_are_k && trans_b) {
+    const int vec = (ldb % 4 == 0 && aligned16(B)) ? 1 : 0;
+    const int64_t work = (int64_t)N * ((K + 3) / 4);
+    int64_t grid = cdiv64(work, 256);
+    if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
+    tc16::split16_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(B, ldb, N, K, (int)t.kp, vec, amax + 1, Bh, Bl);
+  } else {
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + 63) / 64));
+    tc16::split16_transpose_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, amax + 1, Bh, Bl);
+  }
+  GOTEN_CHECK_LAUNCH();
+
+  CUtensorMap mA, mBh, mBl, mC;
+  bool ok;
+  if (!t.a_rows_are_k) ok = make_map_f32(&mA, A, lda, M, K, 32, tc16::BM, CU_TENSOR_MAP_SWIZZLE_128B);
+  else ok = make_map_f32(&mA, A, lda, K, M, tc16::BM, tc16::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+  ok = ok && make_map_f16(&mBh, Bh, t.kp, N, K, t.block_n / t.ncta) && make_map_f16(&mBl, Bl, t.kp, N, K, t.block_n / t.ncta);
+  GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed (fp16 GEMM M=%d N=%d K=%d lda=%d)", M, N, K, lda);
+  const bool fast_epi = t.splits > 1 || ((add_src == nullptr) && (act_out == nullptr));
+  if (t.splits > 1) ok = make_map_f32(&mC, partial, N, (int64_t)t.splits * M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  else if (fast_epi) {
+    if (!aligned16(C) || ldc % 4 != 0) return 0;
+    ok = make_map_f32(&mC, C, ldc, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+  } else mC = mA;
+  GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed for the output (M=%d N=%d ldc=%d)", M, N, ldc);
+
+  tc16::Params p{};
+  p.M = M; p.N = N; p.K = K;
+  p.block_n = t.block_n; p.n_mt = t.n_mt; p.n_nt = t.n_nt;
+  p.splits = t.splits; p.kb_per_split = t.kb_per_split; p.kb_total = t.kb_total;
+  p.stages = t.stages;
+  p.C = C; p.ldc = ldc; p.bias = bias; p.add_src = add_src; p.ld_add = ld_add;
+  p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
+  p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
+  p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
+  p.partial = partial; p.colsum = colsum; p.partial_colsum = partial_cs;
+  p.amax = amax;
+  if (t.splits > 1) { p.bias = nullptr; p.add_src = nullptr; p.act_out = nullptr; }
+
+  const size_t smem = 1024 + (size_t)t.stages * (tc16::A_BYTES + 2 * (size_t)(t.block_n / t.ncta) * tc16::BK * 2) +
+                      4 * 2 * 4096 + (3 * tc16::MAX_STAGES + 4) * 8 + 16;
+  GOTEN_REQUIRE((int)smem <= smem_optin, "tcgen05 fp16 GEMM needs %zu B of shared memory", smem);
+  const int n_items = t.n_mt * t.n_nt * t.splits;
+  const int max_units = sm_count / t.ncta;
+  const int grid = (n_items < max_units ? n_items : max_units) * t.ncta;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tc16::NTHREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)t.ncta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+#define GOTEN_TC16_LAUNCH(RK, NC)                                                                           \
+  do {                                                                                                      \
+    auto k = tc16::gemm16_kernel<RK, NC>;                                                                   \
+    static int smem_set = 0;                                                                                \
+    if ((int)smem > smem_set) {                                                                             \
+      GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));   \
+      smem_set = smem_optin;                                                                                \
+    }                                                                                                       \
+    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, p));                                     \
+  } while (0)
+  if (t.a_rows_are_k) {
+    if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, 2); else GOTEN_TC16_LAUNCH(true, 1);
+  } else {
+    if (t.ncta == 2) GOTEN_TC16_LAUNCH(false, 2); else GOTEN_TC16_LAUNCH(false, 1);
+  }
+#undef GOTEN_TC16_LAUNCH
+  GOTEN_CHECK_LAUNCH();
+  if (t.splits > 1) {
+    if (splitk_finish(partial, partial_cs, t.splits, C, ldc, M, N, bias, add_src, ld_add, act_out, ld_act, act_lo,
+                      act_hi, colsum, st))
+      return 1;
+  }
+  *handled = true;
+  return 0;
+}
+
+}  // namespace goten
+
+using namespace goten;
+
+extern "C" {
+
+int goten_absmax(const float* A, int64_t lda, int64_t M, int N, float* out, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  int dev = 0, sms = 0;
+  GOTEN_CHECK_CUDA(cudaGetDevice(&dev));
+  GOTEN_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  return launch_absmax(A, lda, M, N, out, sms, as_stream(stream));
+}
+
+}  // extern "C"

@@ -149,11 +149,12 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
                                    const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
                                    int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
-                                   float* __restrict__ g_Y) {
+                                   float* __restrict__ g_Y, float* __restrict__ gze_amax) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   __shared__ float red[33];
   const int i = blockIdx.x, c = threadIdx.x * V;
   const bool act = c < C;
+  float amx = 0.f;
   float q[L][V], gq[L][V];
 #pragma unroll
   for (int m = 0; m < L; ++m) {
@@ -180,6 +181,7 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
         col_of<L, V>(gq, qq, gc);
         const float w = htr_weight<LMAX>(qc, kc, y, flags);
         gz[qq] = dt[qq] * w * dsiluf_(zt[qq]);
+        amx = fmaxf(amx, fabsf(gz[qq]));
         const float dw = dt[qq] * siluf_(zt[qq]);
         htr_grad<LMAX>(kc, y, flags, dw, gc);
 #pragma unroll
@@ -212,6 +214,7 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
 #pragma unroll
     for (int m = 0; m < L; ++m) stv<V>(g_EQ + ((size_t)m * N + i) * C + c, gq[m]);
   }
+  amax_commit(gze_amax, amx);
 }
 
 template <int LMAX, int V>
@@ -289,9 +292,9 @@ int goten_htr_fwd(const float* EQ, const float* EK, const float* Y, const float*
 
 int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
-                      float* g_EQ, float* gZe, int ldgz, float* g_Y, void* stream) {
+                      float* g_EQ, float* gZe, int ldgz, float* g_Y, float* gze_amax, void* stream) {
   HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
-               g_Y);
+               g_Y, gze_amax);
 }
 
 int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,

@@ -22,7 +22,7 @@ import torch
 from ._lib import GotenError, lib
 
 _WS = {}
-_IMPL = {"simt": 1, "tc": 2, "auto": 0}
+_IMPL = {"simt": 1, "tc": 2, "tc16": 3, "auto": 0}
 
 
 def gemm_impl() -> int:
@@ -68,28 +68,79 @@ def workspace(nbytes: int, device) -> torch.Tensor:
 # thin kernel wrappers
 # ---------------------------------------------------------------------------
 def gemm(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, *, a_off=0, b_off=0, c_off=0, bias=None, add_src=None,
-         ld_add=0, add_off=0, act_out=None, ld_act=0, act_off=0, act_lo=0, act_hi=0, colsum=None, impl=None):
-    """C[M,N] = op(A) op(B) (+bias) (+add_src); see goten_gemm in the header."""
+         ld_add=0, add_off=0, act_out=None, ld_act=0, act_off=0, act_lo=0, act_hi=0, colsum=None, impl=None,
+         a_amax=None, b_amax=None, am=None):
+    """C[M,N] = op(A) op(B) (+bias) (+add_src); see goten_gemm / goten_gemm_scaled in the header.
+    a_amax / b_amax: optional 1-element device tensors bounding max|A| / max|B| (split-fp16 arm);
+    am: an AmaxScope that supplies (and caches) them for the whole tensors A and B."""
     L = lib()
+    if am is not None and am.enabled:
+        a_amax = am.of(A) if a_amax is None else a_amax
+        b_amax = am.of(B) if b_amax is None else b_amax
     nbytes = L.cdll.goten_gemm_workspace_bytes(M, N, K, ta, tb)
     ws = workspace(nbytes, C.device) if nbytes > 0 else None
-    L.call("goten_gemm", _ptr(A, a_off), lda, ta, _ptr(B, b_off), ldb, tb, _ptr(C, c_off), ldc, M, N, K,
+    L.call("goten_gemm_scaled", _ptr(A, a_off), lda, ta, _ptr(B, b_off), ldb, tb, _ptr(C, c_off), ldc, M, N, K,
            _ptr(bias), _ptr(add_src, add_off), ld_add, _ptr(act_out, act_off), ld_act, act_lo, act_hi,
-           _ptr(colsum), _ptr(ws), nbytes, gemm_impl() if impl is None else impl, _stream())
+           _ptr(colsum), _ptr(a_amax), _ptr(b_amax), _ptr(ws), nbytes, gemm_impl() if impl is None else impl,
+           _stream())
 
 
-def linear_fwd(a, w, b=None, *, act=False):
+def absmax(A, lda, M, N, *, a_off=0, out=None):
+    """1-element device tensor holding max |A[m][n]| (no host sync); accumulates into `out` when given."""
+    if out is None:
+        out = torch.zeros(1, device=A.device, dtype=torch.float32)
+    if M > 0 and N > 0:
+        lib().call("goten_absmax", _ptr(A, a_off), lda, M, N, _ptr(out), _stream())
+    return out
+
+
+class AmaxScope:
+    """max|T| device scalars of the GEMM operands of one forward / backward call, each measured once
+    (goten_absmax, or written by the producing kernel) and shared by every GEMM that reads the tensor;
+    `export` / `load` carry them from a block's forward to its backward.  Only the split-fp16 GEMM arm
+    uses them (operand scaling), so the scope is inert under GOTEN_GEMM=simt|tc or GOTEN_TC16=0."""
+
+    def __init__(self):
+        self.enabled = gemm_impl() in (0, 3) and os.environ.get("GOTEN_TC16", "1") != "0"
+        self._d = {}
+
+    def put(self, T, a):
+        if T is not None and a is not None:
+            self._d[T.data_ptr()] = (T, a)
+
+    def of(self, T):
+        ent = self._d.get(T.data_ptr())
+        if ent is None:
+            cols = T.shape[-1]
+            ent = (T, absmax(T, cols, T.numel() // max(cols, 1), cols))
+            self._d[T.data_ptr()] = ent
+        return ent[1]
+
+    def export(self, tensors):
+        """amax tensors (or an empty list when inert) of `tensors`, in order; None entries are skipped."""
+        if not self.enabled:
+            return []
+        return [self.of(T) for T in tensors if T is not None]
+
+    def load(self, tensors, amaxes):
+        if not self.enabled or not amaxes:
+            return
+        for T, a in zip([T for T in tensors if T is not None], amaxes):
+            self.put(T, a)
+
+
+def linear_fwd(a, w, b=None, *, act=False, am=None):
     """z = a w^T + b ; returns (z, silu(z)) if act else z.   a [M,K], w [N,K]."""
     _chk(a, w, b)
     M, K = a.shape
     N = w.shape[0]
     z = torch.empty(M, N, device=a.device, dtype=torch.float32)
     y = torch.empty_like(z) if act else None
-    gemm(a, K, 0, w, K, 1, z, N, M, N, K, bias=b, act_out=y, ld_act=N, act_lo=0, act_hi=N if act else 0)
+    gemm(a, K, 0, w, K, 1, z, N, M, N, K, bias=b, act_out=y, ld_act=N, act_lo=0, act_hi=N if act else 0, am=am)
     return (z, y) if act else z
 
 
-def linear_bwd(g, a, w, *, need_da=True, need_bias=True, add_src=None):
+def linear_bwd(g, a, w, *, need_da=True, need_bias=True, add_src=None, am=None):
     """g [M,N] gradient of z = a w^T + b.  Returns (da [M,K] (+add_src), dw [N,K], db [N])."""
     _chk(g, a, w)
     M, N = g.shape
@@ -97,10 +148,10 @@ def linear_bwd(g, a, w, *, need_da=True, need_bias=True, add_src=None):
     da = None
     if need_da:
         da = torch.empty(M, K, device=g.device, dtype=torch.float32)
-        gemm(g, N, 0, w, K, 0, da, K, M, K, N, add_src=add_src, ld_add=K)
+        gemm(g, N, 0, w, K, 0, da, K, M, K, N, add_src=add_src, ld_add=K, am=am)
     dw = torch.empty(N, K, device=g.device, dtype=torch.float32)
     db = torch.empty(N, device=g.device, dtype=torch.float32) if need_bias else None
-    gemm(g, N, 1, a, K, 0, dw, K, N, K, M, colsum=db)
+    gemm(g, N, 1, a, K, 0, dw, K, N, K, M, colsum=db, am=am)
     return da, dw, db
 
 
@@ -315,19 +366,20 @@ class GataBlockFn(torch.autograd.Function):
         ldz = We.shape[0]
         dev = h.device
         SC = S * C
+        am = AmaxScope()
         # node projections: Z1 = [q | k | pre_s | pre_v], A1 = silu(Z1[:, 2C:])
         Z1 = torch.empty(N, 4 * C, device=dev)
         A1 = torch.empty(N, 2 * C, device=dev)
         gemm(h, C, 0, Wn1, C, 1, Z1, 4 * C, N, 4 * C, C, bias=bn1, act_out=A1, ld_act=2 * C, act_lo=2 * C,
-             act_hi=4 * C)
+             act_hi=4 * C, am=am)
         x = torch.empty(N, SC, device=dev)
         v = torch.empty(N, SC, device=dev)
-        gemm(A1, 2 * C, 0, Ws2, C, 1, x, SC, N, SC, C, bias=bs2)
-        gemm(A1, 2 * C, 0, Wv2, C, 1, v, SC, N, SC, C, bias=bv2, a_off=C)
+        gemm(A1, 2 * C, 0, Ws2, C, 1, x, SC, N, SC, C, bias=bs2, am=am)
+        gemm(A1, 2 * C, 0, Wv2, C, 1, v, SC, N, SC, C, bias=bv2, a_off=C, am=am)
         # edge projections (pre-activations; consumers apply SiLU)
         Ze = torch.empty(E, ldz, device=dev)
         if E > 0:
-            gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be)
+            gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, am=am)
         h1 = torch.empty_like(h)
         Xd1 = torch.empty_like(Xd)
         alpha = torch.empty(E, H, device=dev)
@@ -339,15 +391,18 @@ class GataBlockFn(torch.autograd.Function):
         if htr:
             EQ = torch.empty_like(Xd1)
             EK = torch.empty_like(Xd1)
-            gemm(Xd1, C, 0, Wvq, C, 1, EQ, C, L * N, C, C)
+            gemm(Xd1, C, 0, Wvq, C, 1, EQ, C, L * N, C, C, am=am)
             for g, (lo, hi) in enumerate(cfg["vk_groups"]):
                 rows = (hi - lo) * N
-                gemm(Xd1, C, 0, Wvk, C, 1, EK, C, rows, C, C, a_off=lo * N * C, b_off=g * C * C, c_off=lo * N * C)
+                gemm(Xd1, C, 0, Wvk, C, 1, EK, C, rows, C, C, a_off=lo * N * C, b_off=g * C * C, c_off=lo * N * C, am=am)
             t1 = torch.empty_like(t)
             L_.call("goten_htr_fwd", _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, (S + 1) * C, _ptr(t),
                     _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(t1), st)
         ctx.plan, ctx.cfg, ctx.htr = plan, cfg, htr
-        ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK)
+        amx = am.export([h, t, Wn1, Ws2, Wv2, We, Wvq, Wvk, A1, Xd1 if htr else None])
+        ctx.n_amax = len(amx)
+        ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK,
+                              *amx)
         if htr:
             return h1, Xd1, t1
         return h1, Xd1  # last layer: t_ij passes through unchanged (gotennet.py:449-450)
@@ -355,8 +410,11 @@ class GataBlockFn(torch.autograd.Function):
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_h1, g_Xd1, g_t1=None):
-        (h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK) = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        (h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK) = saved[:21]
         plan, cfg, htr = ctx.plan, ctx.cfg, ctx.htr
+        am = AmaxScope()
+        am.load([h, t, Wn1, Ws2, Wv2, We, Wvq, Wvk, A1, Xd1 if htr else None], saved[21:21 + ctx.n_amax])
         L_ = lib()
         st = _stream()
         N, C = h.shape
@@ -372,6 +430,8 @@ class GataBlockFn(torch.autograd.Function):
         if g_t1 is not None:
             g_t1 = g_t1.contiguous()
         gZe = torch.empty(E, ldz, device=dev)
+        gze_amax = torch.zeros(1, device=dev) if am.enabled else None  # written by the two kernels that fill gZe
+        am.put(gZe, gze_amax)
         g_Y = torch.zeros(E, L, device=dev) if need_gY else None
         g_fc = torch.zeros(E, device=dev) if need_gfc else None
         dWvq = dWvk = None
@@ -384,28 +444,28 @@ class GataBlockFn(torch.autograd.Function):
             zt0 = (S + 1) * C
             L_.call("goten_htr_bwd_tgt", _ptr(g_t1), _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, zt0,
                     _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(g_EQ), _ptr(gZe), ldz,
-                    _ptr(g_Y), st)
+                    _ptr(g_Y), _ptr(gze_amax), st)
             L_.call("goten_htr_bwd_src", _ptr(g_t1), _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, zt0,
                     _ptr(plan.src_ptr), _ptr(plan.src_perm), _ptr(plan.tgt), N, C, lmax, cfg["htr_flags"],
                     _ptr(g_EK), st)
             # X gradient: g_Xm = g_Xd1 + g_EQ Wvq + g_EK^l Wvk_l ; weight gradients
             g_Xm = torch.empty_like(Xd1)
-            gemm(g_EQ, C, 0, Wvq, C, 0, g_Xm, C, L * N, C, C, add_src=g_Xd1, ld_add=C)
+            gemm(g_EQ, C, 0, Wvq, C, 0, g_Xm, C, L * N, C, C, add_src=g_Xd1, ld_add=C, am=am)
             dWvq = torch.empty_like(Wvq)
-            gemm(g_EQ, C, 1, Xd1, C, 0, dWvq, C, C, C, L * N)
+            gemm(g_EQ, C, 1, Xd1, C, 0, dWvq, C, C, C, L * N, am=am)
             dWvk = torch.empty_like(Wvk)
             for g, (lo, hi) in enumerate(cfg["vk_groups"]):
                 rows, off = (hi - lo) * N, lo * N * C
                 gemm(g_EK, C, 0, Wvk, C, 0, g_Xm, C, rows, C, C, a_off=off, b_off=g * C * C, c_off=off,
-                     add_src=g_Xm, ld_add=C, add_off=off)
-                gemm(g_EK, C, 1, Xd1, C, 0, dWvk, C, C, C, rows, a_off=off, b_off=off, c_off=g * C * C)
+                     add_src=g_Xm, ld_add=C, add_off=off, am=am)
+                gemm(g_EK, C, 1, Xd1, C, 0, dWvk, C, C, C, rows, a_off=off, b_off=off, c_off=g * C * C, am=am)
         # message block
         g_Z1 = torch.empty(N, 4 * C, device=dev)
         da = torch.empty(E, H, device=dev)
         L_.call("goten_gata_bwd_tgt", _ptr(g_h1), _ptr(g_Xm), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze),
                 ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(alpha), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax,
                 cfg["gata_flags"], plan.max_deg_in, _ptr(g_Z1), 4 * C, _ptr(gZe), ldz, _ptr(da), _ptr(g_fc),
-                _ptr(g_Y), st)
+                _ptr(g_Y), _ptr(gze_amax), st)
         g_x = torch.empty(N, SC, device=dev)
         g_v = torch.empty(N, SC, device=dev)
         g_Xd = torch.empty_like(Xd)
@@ -415,28 +475,28 @@ class GataBlockFn(torch.autograd.Function):
                 _ptr(g_Xd), st)
         # gamma_s.1 / gamma_v.1
         g_A1 = torch.empty(N, 2 * C, device=dev)
-        gemm(g_x, SC, 0, Ws2, C, 0, g_A1, 2 * C, N, C, SC)
-        gemm(g_v, SC, 0, Wv2, C, 0, g_A1, 2 * C, N, C, SC, c_off=C)
+        gemm(g_x, SC, 0, Ws2, C, 0, g_A1, 2 * C, N, C, SC, am=am)
+        gemm(g_v, SC, 0, Wv2, C, 0, g_A1, 2 * C, N, C, SC, c_off=C, am=am)
         dWs2 = torch.empty_like(Ws2)
         dbs2 = torch.empty(SC, device=dev)
-        gemm(g_x, SC, 1, A1, 2 * C, 0, dWs2, C, SC, C, N, colsum=dbs2)
+        gemm(g_x, SC, 1, A1, 2 * C, 0, dWs2, C, SC, C, N, colsum=dbs2, am=am)
         dWv2 = torch.empty_like(Wv2)
         dbv2 = torch.empty(SC, device=dev)
-        gemm(g_v, SC, 1, A1, 2 * C, 0, dWv2, C, SC, C, N, b_off=C, colsum=dbv2)
+        gemm(g_v, SC, 1, A1, 2 * C, 0, dWv2, C, SC, C, N, b_off=C, colsum=dbv2, am=am)
         # through the SiLU of gamma_s.0 / gamma_v.0 into g_Z1[:, 2C:4C]
         dsilu_mul(g_A1, 2 * C, 0, Z1, 4 * C, 2 * C, g_Z1, 4 * C, 2 * C, N, 2 * C)
         g_h = torch.empty_like(h)
-        gemm(g_Z1, 4 * C, 0, Wn1, C, 0, g_h, C, N, C, 4 * C, add_src=g_h1, ld_add=C)
+        gemm(g_Z1, 4 * C, 0, Wn1, C, 0, g_h, C, N, C, 4 * C, add_src=g_h1, ld_add=C, am=am)
         dWn1 = torch.empty_like(Wn1)
         dbn1 = torch.empty(4 * C, device=dev)
-        gemm(g_Z1, 4 * C, 1, h, C, 0, dWn1, C, 4 * C, C, N, colsum=dbn1)
+        gemm(g_Z1, 4 * C, 1, h, C, 0, dWn1, C, 4 * C, C, N, colsum=dbn1, am=am)
         # edge projections
         g_t = torch.empty_like(t)
         dWe = torch.empty_like(We)
         dbe = torch.empty(ldz, device=dev)
         if E > 0:
-            gemm(gZe, ldz, 0, We, C, 0, g_t, C, E, C, ldz, add_src=g_t1, ld_add=C)
-            gemm(gZe, ldz, 1, t, C, 0, dWe, C, ldz, C, E, colsum=dbe)
+            gemm(gZe, ldz, 0, We, C, 0, g_t, C, E, C, ldz, add_src=g_t1, ld_add=C, am=am)
+            gemm(gZe, ldz, 1, t, C, 0, dWe, C, ldz, C, E, colsum=dbe, am=am)
         else:
             dWe.zero_()
             dbe.zero_()
@@ -455,22 +515,28 @@ class EqffBlockFn(torch.autograd.Function):
         N, C = h.shape
         L = Xd.shape[0]
         dev = h.device
+        am = AmaxScope()
         P = torch.empty_like(Xd)
-        gemm(Xd, C, 0, Wvu, C, 1, P, C, L * N, C, C)
+        gemm(Xd, C, 0, Wvu, C, 1, P, C, L * N, C, C, am=am)
         cx = torch.empty(N, 2 * C, device=dev)
         L_.call("goten_eqff_ctx_fwd", _ptr(h), _ptr(P), N, C, L, float(eps), _ptr(cx), st)
-        Zm, Am = linear_fwd(cx, Wm1, bm1, act=True)
-        M = linear_fwd(Am, Wm2, bm2)
+        Zm, Am = linear_fwd(cx, Wm1, bm1, act=True, am=am)
+        M = linear_fwd(Am, Wm2, bm2, am=am)
         h2 = torch.empty_like(h)
         Xd2 = torch.empty_like(Xd)
         L_.call("goten_eqff_update_fwd", _ptr(h), _ptr(Xd), _ptr(P), _ptr(M), N, C, L, _ptr(h2), _ptr(Xd2), st)
-        ctx.save_for_backward(Xd, Wvu, Wm1, Wm2, P, cx, Zm, Am, M)
+        amx = am.export([Xd, Wvu, Wm1, Wm2, cx, Am])
+        ctx.n_amax = len(amx)
+        ctx.save_for_backward(Xd, Wvu, Wm1, Wm2, P, cx, Zm, Am, M, *amx)
         return h2, Xd2
 
     @staticmethod
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_h2, g_Xd2):
-        Xd, Wvu, Wm1, Wm2, P, cx, Zm, Am, M = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        Xd, Wvu, Wm1, Wm2, P, cx, Zm, Am, M = saved[:9]
+        am = AmaxScope()
+        am.load([Xd, Wvu, Wm1, Wm2, cx, Am], saved[9:9 + ctx.n_amax])
         L_ = lib()
         st = _stream()
         L, N, C = Xd.shape
@@ -479,18 +545,18 @@ class EqffBlockFn(torch.autograd.Function):
         g_Xd2 = g_Xd2.contiguous() if g_Xd2 is not None else torch.zeros(L, N, C, device=dev)
         g_M = torch.empty(N, 2 * C, device=dev)
         L_.call("goten_eqff_update_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(P), N, C, L, _ptr(g_M), st)
-        g_Am, dWm2, dbm2 = linear_bwd(g_M, Am, Wm2)
+        g_Am, dWm2, dbm2 = linear_bwd(g_M, Am, Wm2, am=am)
         g_Zm = torch.empty_like(g_Am)
         dsilu_mul(g_Am, C, 0, Zm, C, 0, g_Zm, C, 0, N, C)
-        g_cx, dWm1, dbm1 = linear_bwd(g_Zm, cx, Wm1)
+        g_cx, dWm1, dbm1 = linear_bwd(g_Zm, cx, Wm1, am=am)
         g_P = torch.empty_like(P)
         g_h = torch.empty(N, C, device=dev)
         L_.call("goten_eqff_ctx_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(g_cx), _ptr(P), _ptr(M), _ptr(cx), N, C, L,
                 _ptr(g_P), _ptr(g_h), st)
         g_Xd = torch.empty_like(Xd)
-        gemm(g_P, C, 0, Wvu, C, 0, g_Xd, C, L * N, C, C, add_src=g_Xd2, ld_add=C)
+        gemm(g_P, C, 0, Wvu, C, 0, g_Xd, C, L * N, C, C, add_src=g_Xd2, ld_add=C, am=am)
         dWvu = torch.empty_like(Wvu)
-        gemm(g_P, C, 1, Xd, C, 0, dWvu, C, C, C, L * N)
+        gemm(g_P, C, 1, Xd, C, 0, dWvu, C, C, C, L * N, am=am)
         return g_h, g_Xd, dWvu, dWm1, dbm1, dWm2, dbm2, None
 
 

@@ -112,12 +112,25 @@ int goten_edge_vec_to_pos_bwd(const float* g_vec, const int32_t* tgt_ptr, const 
  *   colsum != NULL (trans_a = 1 only): colsum[m] = sum_k A[k][m]  (bias gradient
  *     fused into the weight-gradient GEMM).
  * `workspace` (split-K partials): at least goten_gemm_workspace_bytes(...) bytes.
- * impl: 0 = auto, 1 = fp32 SIMT, 2 = tcgen05 3xTF32.                            */
+ * impl: 0 = auto (first arm that accepts the shape, in the order 3, 2, 1), 1 = fp32 SIMT,
+ *       2 = tcgen05 3xTF32, 3 = tcgen05 split-fp16 (x*2^s = hi + lo in fp16, three
+ *       kind::f16 MMAs, fp32 accumulation; 22 significant bits).
+ * goten_gemm_scaled: same, with optional DEVICE pointers to an upper bound of max|A| /
+ *   max|B| (within a few powers of two of the true maximum) used by arm 3 for its
+ *   power-of-two operand scaling; NULL = measured inside the call by one read pass.     */
 int64_t goten_gemm_workspace_bytes(int M, int N, int K, int trans_a, int trans_b);
 int goten_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,
                float* C, int ldc, int M, int N, int K, const float* bias, const float* add_src,
                int ld_add, float* act_out, int ld_act, int act_lo, int act_hi, float* colsum,
                void* workspace, int64_t workspace_bytes, int impl, void* stream);
+int goten_gemm_scaled(const float* A, int lda, int trans_a, const float* B, int ldb, int trans_b,
+                      float* C, int ldc, int M, int N, int K, const float* bias,
+                      const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo,
+                      int act_hi, float* colsum, const float* a_amax, const float* b_amax,
+                      void* workspace, int64_t workspace_bytes, int impl, void* stream);
+/* out[0] = max(out[0], max |A[m][n]|) over a [M][N] matrix (ld = lda); out must hold a
+ * non-negative float (zero it first for a plain maximum).                                */
+int goten_absmax(const float* A, int64_t lda, int64_t M, int N, float* out, void* stream);
 /* out[m][n] = g[m][n] * silu'(pre[m][n])  (Dense activation backward, layers.py:527-528) */
 int goten_dsilu_mul(const float* g, int ldg, const float* pre, int ldp, float* out, int ldo,
                     int64_t M, int N, void* stream);
@@ -173,13 +186,15 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
 /* backward, target-centric half: needs g_h[N][C], g_Xd[L][N][C] (gradients of the
  * block outputs).  Produces g_qk[:, 0:C) (dq), gZe[:, 0:(S+1)C) (d pre-act W_re, d filter),
  * da[E][H] (gradient of the attention logits) and, if non-NULL, the geometry
- * gradients g_fc[E] (accumulated) and g_Y[E][L] (accumulated).                 */
+ * gradients g_fc[E] (accumulated) and g_Y[E][L] (accumulated).  gze_amax (optional,
+ * device): running max |value written to gZe| (atomic max on a non-negative float; the
+ * caller zeroes it), consumed by goten_gemm_scaled.                               */
 int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, const float* qk,
                        int ldqk, const float* x, const float* v, const float* Ze, int ldz,
                        const float* Y, const float* fc, const float* kappa, const float* alpha,
                        const int32_t* tgt_ptr, const int32_t* src, int n_nodes, int C, int H,
                        int lmax, int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe,
-                       int ldgz, float* da, float* g_fc, float* g_Y, void* stream);
+                       int ldgz, float* da, float* g_fc, float* g_Y, float* gze_amax, void* stream);
 /* backward, source-centric half: g_qk[:, C:2C) (dk), g_x, g_v [N][S*C] and
  * g_Xd_in[L][N][C] = g_Xd + sum over outgoing edges (residual included).      */
 int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, const float* qk,
@@ -202,7 +217,7 @@ int goten_htr_fwd(const float* EQ, const float* EK, const float* Y, const float*
 int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, const float* Y,
                       const float* Ze, int ldz, int zt_col0, const int32_t* tgt_ptr,
                       const int32_t* src, int n_nodes, int C, int lmax, int flags, float* g_EQ,
-                      float* gZe, int ldgz, float* g_Y, void* stream);
+                      float* gZe, int ldgz, float* g_Y, float* gze_amax, void* stream);
 /* source half: g_EK[L][N][C] */
 int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, const float* Y,
                       const float* Ze, int ldz, int zt_col0, const int32_t* src_ptr,

@@ -1,5 +1,6 @@
-"""GPU: accuracy and speed of the tcgen05 3xTF32 GEMM arm vs the fp32 SIMT arm (both through goten_gemm).
-    python tests/gpu_gemm_check.py [quick]"""
+"""GPU: accuracy and speed of the tensor-core GEMM arms (2 = tcgen05 3xTF32, 3 = tcgen05 split-fp16) vs the
+fp32 SIMT arm (1), all through goten_gemm_scaled.  Exploration tool, not collected by pytest.
+    python tests/gpu_gemm_check.py [quick] [impls=1,2,3] [scale=1e-6]"""
 import os
 import sys
 
@@ -27,16 +28,28 @@ def timeit(fn, n=5):
     return e0.elapsed_time(e1) / n
 
 
+IMPLS = (1, 2, 3)
+SCALE = 1.0
+for a_ in sys.argv[1:]:
+    if a_.startswith("impls="):
+        IMPLS = tuple(int(x) for x in a_[6:].split(","))
+    if a_.startswith("scale="):
+        SCALE = float(a_[6:])
+
+
 def check(M, N, K, perf=False):
     g = torch.Generator(device="cpu").manual_seed(M + 3 * N + 7 * K)
     a = (torch.randn(M, K, generator=g)).to(dev)
     w = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
     b = torch.randn(N, generator=g).to(dev)
     add = torch.randn(M, N, generator=g).to(dev)
-    gr = torch.randn(M, N, generator=g).to(dev)
+    gr = (torch.randn(M, N, generator=g) * SCALE).to(dev)
+    if SCALE != 1.0:  # wide dynamic range inside the tensors: a few large outliers
+        a[::7, ::5] *= 300.0
+        gr[::3, ::11] *= 1e-4
     exact = M * N * K < 3e10
     out = {}
-    for impl in (1, 2):
+    for impl in IMPLS:
         y = torch.empty(M, N, device=dev)
         act = torch.empty(M, N, device=dev)
         da = torch.empty(M, K, device=dev)
@@ -65,14 +78,16 @@ def check(M, N, K, perf=False):
             msg += "  TF/s: " + " ".join(f"{nm} {fl / (timeit(f) * 1e-3) / 1e12:.1f}" for nm, f in
                                         (("NT", f_nt), ("NN", f_nn), ("TN", f_tn)))
         print(msg, flush=True)
-    if 1 in out and 2 in out and not exact:
-        print("  tc vs simt:", " ".join(f"{rel(x, y_.double()):.1e}" for x, y_ in zip(out[2], out[1])))
+    if not exact:
+        for i in IMPLS[1:]:
+            if IMPLS[0] in out and i in out:
+                print(f"  impl {i} vs {IMPLS[0]}:", " ".join(f"{rel(x, y_.double()):.1e}" for x, y_ in zip(out[i], out[IMPLS[0]])))
 
 
 if __name__ == "__main__":
-    quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
+    quick = "quick" in sys.argv[1:]
     shapes = [(128, 256, 32, False), (1000, 256, 256, False), (4096, 1792, 256, False), (333, 64, 64, False),
-              (2048, 96, 160, False)]
+              (2048, 96, 160, False), (777, 256, 1000, False), (4099, 512, 72, False)]
     if not quick:
         shapes += [(301491, 1792, 256, True), (147768, 256, 256, True), (18471, 1024, 256, True)]
     for M, N, K, perf in shapes:

@@ -90,8 +90,12 @@ def test_radius_graph_edge_cases(g, dev):
 
 # ------------------------------------------------------------------- GEMM -----
 @pytest.mark.parametrize("M,N,K", [(1000, 130, 37), (257, 256, 256), (4096, 1792, 256), (33, 5, 3)])
-@pytest.mark.parametrize("impl", [1, 0])
+@pytest.mark.parametrize("impl", [1, 0, 2, 3])
 def test_gemm_layouts(g, dev, M, N, K, impl):
+    if impl in (2, 3) and N < 16:
+        pytest.skip("tensor-core arms need N >= 16 (auto falls through to the SIMT arm)")
+    if impl == 2 and (M % 32 or N % 32 or K % 32):
+        pytest.skip("the 3xTF32 arm rejects the unaligned weight-gradient form")
     from gotennet_b200 import ops
     gen = torch.Generator().manual_seed(M + N + K)
     a = torch.randn(M, K, generator=gen)
@@ -102,8 +106,8 @@ def test_gemm_layouts(g, dev, M, N, K, impl):
     A, W, B, ADD = a.to(dev), w.to(dev), b.to(dev), add.to(dev)
     out = torch.empty(M, N, device=dev)
     act = torch.empty(M, N, device=dev)
-    # impl 1 = exact-fp32 SIMT; impl 0 = auto (tcgen05 3xTF32 where the shape allows): the tensor core
-    # accumulates with truncation, ~2e-8 relative per accumulating MMA (gemm_tc.cu), hence the looser bound
+    # impl 1 = exact-fp32 SIMT; 2 = tcgen05 3xTF32; 3 = tcgen05 split-fp16; 0 = auto (3, 2, 1 in that order, first arm
+    # that accepts the shape): the tensor core accumulates with truncation, ~2e-8 relative per accumulating MMA (gemm_tc.cu), hence the looser bound
     tol = 2e-6 if impl == 1 else 2e-5
     ops.gemm(A, K, 0, W, K, 1, out, N, M, N, K, bias=B, add_src=ADD, ld_add=N, act_out=act, ld_act=N, act_lo=0,
              act_hi=N, impl=impl)
@@ -126,6 +130,41 @@ def test_gemm_layouts(g, dev, M, N, K, impl):
     out2 = torch.empty(M, N, device=dev)
     ops.gemm(wide, 3 * K, 0, W, K, 1, out2, N, M, N, K, a_off=K, impl=impl)
     assert rel(out2, wide[:, K:2 * K].double().cpu() @ w.double().T) < tol
+
+
+def test_gemm_fp16_split_dynamic_range(g, dev):
+    """Split-fp16 arm: per-tensor power-of-two scaling keeps fp32-class accuracy for tiny gradients, for a few
+    huge outliers inside a tensor, and with caller-supplied (loose) operand bounds; goten_absmax is exact."""
+    from gotennet_b200 import ops
+    gen = torch.Generator().manual_seed(7)
+    M, N, K = 3000, 320, 264
+    a = torch.randn(M, K, generator=gen)
+    a[::7, ::5] *= 3e3                       # outliers: 3.5 decades above the bulk
+    w = torch.randn(N, K, generator=gen) * 1e-3
+    gr = torch.randn(M, N, generator=gen) * 1e-9   # far below the fp16 normal range before scaling
+    gr[::3, ::11] *= 1e-4
+    A, W, G = a.to(dev), w.to(dev), gr.to(dev)
+    am = ops.absmax(A, K, M, K)
+    assert float(am) == float(a.abs().max())
+    out = torch.empty(M, N, device=dev)
+    ops.gemm(A, K, 0, W, K, 1, out, N, M, N, K, impl=3)
+    assert rel(out, a.double() @ w.double().T) < 2e-6
+    da = torch.empty(M, K, device=dev)
+    ops.gemm(G, N, 0, W, K, 0, da, K, M, K, N, impl=3)
+    assert rel(da, gr.double() @ w.double()) < 2e-6
+    dw = torch.empty(N, K, device=dev)
+    db = torch.empty(N, device=dev)
+    ops.gemm(G, N, 1, A, K, 0, dw, K, N, K, M, colsum=db, impl=3)
+    assert rel(dw, gr.double().T @ a.double()) < 2e-6
+    assert rel(db, gr.double().sum(0)) < 2e-6
+    # bounds 2^6 above the true maxima: still far inside the fp32 class
+    out2 = torch.empty(M, N, device=dev)
+    ops.gemm(A, K, 0, W, K, 1, out2, N, M, N, K, impl=3, a_amax=am * 64, b_amax=ops.absmax(W, K, N, K) * 64)
+    assert rel(out2, a.double() @ w.double().T) < 2e-6
+    # all-zero operand
+    Z = torch.zeros(M, K, device=dev)
+    ops.gemm(Z, K, 0, W, K, 1, out2, N, M, N, K, impl=3)
+    assert float(out2.abs().max()) == 0.0
 
 
 # ------------------------------------------------------- golden vectors -------
