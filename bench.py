@@ -161,6 +161,10 @@ def kernel_report(prof, n_steps, N, E, peaks, ms_step):
                  "bf16 MMA slots, so the ceiling of this kernel is peak/6; achieved*6/peak is its tensor-pipe fraction"),
         "tensor_pipe_frac": achieved * mma_per_product / bf16,
     }
+    shapes = [{"M": k[0], "N": k[1], "K": k[2], "trans": [k[3], k[4]], "launches_per_step": c // n_steps,
+               "ms_per_step": ms_ / n_steps, "tflops": 2.0 * k[0] * k[1] * k[2] * c / (ms_ * 1e-3) / 1e12}
+              for k, (c, ms_) in sorted(gemm_shapes.items(), key=lambda kv: -kv[1][1])[:14]]
+    roofline["gemm_shapes"] = shapes
     return roofline, kernels
 
 # -------------------------------------------------------------- our arm -------

@@ -92,7 +92,9 @@ struct Params {
   const float* amax;      // [0] = max |A|, [1] = max |B| (device)
 };
 
-template <bool A_ROWS_ARE_K, int NCTA>
+// B_RAW (weight-gradient form only): B is staged as raw fp32 [64 k][BNH n] like A and converted in place by the
+// converter warps, so no pre-split copy of the (activation-sized) B operand is written to / re-read from HBM.
+template <bool A_ROWS_ARE_K, bool B_RAW, int NCTA>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC, const Params p) {
@@ -167,8 +169,12 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // A[R][M]: one un-swizzled box of [64 k rows][128 floats]
             tma_load_2d(sa, &tmA, bar, m0, kb * BK);
           }
-          tma_load_2d(sbh, &tmBh, bar, kb * BK, n0);
-          tma_load_2d(sbl, &tmBl, bar, kb * BK, n0);
+          if (B_RAW) {
+            tma_load_2d(sbh, &tmBh, bar, n0, kb * BK);   // tmBh = fp32 map over B[R][N]: box [64 k][BNH n]
+          } else {
+            tma_load_2d(sbh, &tmBh, bar, kb * BK, n0);
+            tma_load_2d(sbl, &tmBl, bar, kb * BK, n0);
+          }
         }
       }
     }
@@ -216,6 +222,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // =============================== converter ==================================
     const int ct = threadIdx.x - CONV_WARP0 * 32;  // 0..127 = tile row (M index) this thread produces
     const float sA = scale_of(p.amax[0]);
+    const float sB = scale_of(p.amax[1]);
     const uint32_t sw = (uint32_t)(ct & 7);
     uint32_t it = 0;
     for (int w = unit; w < n_items; w += n_units) {
@@ -270,6 +277,31 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           if (do_cs) {
 #pragma unroll
             for (int k = 0; k < BK; ++k) csum += v[k];
+          }
+          if (B_RAW) {
+            // same transposing split for column ct of the raw B tile (BNH <= 128 columns, row pitch BNH floats)
+            uint8_t* b_raw = a_raw + A_BYTES;
+            const bool mine = ct < BNH;
+            if (mine) {
+#pragma unroll
+              for (int k = 0; k < BK; ++k) v[k] = *reinterpret_cast<const float*>(b_raw + (size_t)k * BNH * 4 + ct * 4);
+            }
+            conv_bar_sync();
+            if (mine) {
+              uint8_t* bh_row = b_raw + ct * 128;
+              uint8_t* bl_row = bh_row + B_BYTES;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                uint4 h, l;
+                split2(v[8 * c + 0] * sB, v[8 * c + 1] * sB, h.x, l.x);
+                split2(v[8 * c + 2] * sB, v[8 * c + 3] * sB, h.y, l.y);
+                split2(v[8 * c + 4] * sB, v[8 * c + 5] * sB, h.z, l.z);
+                split2(v[8 * c + 6] * sB, v[8 * c + 7] * sB, h.w, l.w);
+                const uint32_t off = (((uint32_t)c ^ sw) << 4);
+                *reinterpret_cast<uint4*>(bh_row + off) = h;
+                *reinterpret_cast<uint4*>(bl_row + off) = l;
+              }
+            }
           }
         }
         fence_proxy_async();
@@ -488,6 +520,31 @@ split16_transpose_kernel(const float* __restrict__ in, int ld, int rows /*K*/, i
   }
 }
 
+// Same transposition without shared memory, for activation-sized B: thread = one output row c and 16 consecutive k;
+// a warp reads 16 coalesced 128 B row segments and every lane writes whole 32 B sectors of its hi / lo rows.
+__global__ void __launch_bounds__(256)
+split16_transpose_direct_kernel(const float* __restrict__ in, int ld, int rows /*K*/, int cols /*N*/, int Kp,
+                                const float* __restrict__ amax, __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float s = scale_of(*amax);
+  const int c = blockIdx.y * 256 + threadIdx.x;
+  const int r0 = blockIdx.x * 16;
+  if (c >= cols) return;
+  float v[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = (r0 + i < rows) ? in[(int64_t)(r0 + i) * ld + c] * s : 0.f;
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {
+    if (r0 + 8 * g >= Kp) break;
+    uint4 h, l;
+    split2(v[8 * g + 0], v[8 * g + 1], h.x, l.x);
+    split2(v[8 * g + 2], v[8 * g + 3], h.y, l.y);
+    split2(v[8 * g + 4], v[8 * g + 5], h.z, l.z);
+    split2(v[8 * g + 6], v[8 * g + 7], h.w, l.w);
+    *reinterpret_cast<uint4*>(hi + (int64_t)c * Kp + r0 + 8 * g) = h;
+    *reinterpret_cast<uint4*>(lo + (int64_t)c * Kp + r0 + 8 * g) = l;
+  }
+}
+
 }  // namespace tc16
 
 int splitk_finish(const float* partial, const float* partial_cs, int splits, float* C, int ldc, int M, int N,
@@ -525,6 +582,7 @@ struct Tc16Plan {
   bool a_rows_are_k;     // weight-gradient form: A given as [R][M]
   int block_n, n_mt, n_nt, splits, kb_total, kb_per_split;
   int ncta, stages;
+  bool b_raw;            // weight-gradient form with B staged raw and converted in the kernel
   int64_t kp;            // padded K of the pre-split B copies (multiple of 8 halves = 16 B)
   int64_t b_bytes;       // bytes of each pre-split B copy
   int64_t ws_bytes;
@@ -564,6 +622,11 @@ static Tc16Plan tc16_plan(int M, int N, int K, int trans_a, int trans_b) {
   t.kb_per_split = (t.kb_total + t.splits - 1) / t.splits;
   t.splits = (t.kb_total + t.kb_per_split - 1) / t.kb_per_split;
   t.kp = ((int64_t)K + 7) & ~int64_t(7);
+  // Weight-gradient form with a single row of M tiles: every B tile is consumed exactly once, so the kernel converts
+  // it in place (no pre-split copy through HBM).  With several M tiles the kernel is shared-memory-bandwidth bound and
+  // re-converting B per M tile costs more than the one pre-split pass (measured: 1792 x 256 x 301k, 0.94 -> 1.00 ms).
+  // Needs one tile column per converter thread (BNH <= 128) and a TMA-addressable B (checked at launch).
+  t.b_raw = t.a_rows_are_k && t.n_mt == 1 && t.block_n / t.ncta <= 128;
   t.b_bytes = align256((int64_t)N * t.kp * 2);
   t.ws_bytes = 256 + 2 * t.b_bytes;
   if (t.splits > 1) t.ws_bytes += align256((int64_t)t.splits * ((int64_t)M * N + M) * 4);
@@ -597,6 +660,7 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   Tc16Plan t = tc16_plan(M, N, K, trans_a, trans_b);
   if (!t.ok || workspace == nullptr || workspace_bytes < t.ws_bytes) return 0;
   if (!aligned16(A) || lda % 4 != 0) return 0;
+  if (t.b_raw && (!aligned16(B) || ldb % 4 != 0)) t.b_raw = false;
   if (colsum && !t.a_rows_are_k) return 0;
   if (get_encode() == nullptr) return 0;
   static int sm_count = 0, smem_optin = 0;
@@ -636,24 +700,35 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     }
   }
 
-  // ---- B operand: scaled fp16 hi / lo copies, K-major [N][Kp]
-  if (!t.a_rows_are_k && trans_b) {
+  // ---- B operand: scaled fp16 hi / lo copies, K-major [N][Kp] (weights); the weight-gradient form converts B in the kernel
+  if (t.b_raw) {
+  } else if (!t.a_rows_are_k && trans_b) {
     const int vec = (ldb % 4 == 0 && aligned16(B)) ? 1 : 0;
     const int64_t work = (int64_t)N * ((K + 3) / 4);
     int64_t grid = cdiv64(work, 256);
     if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
     tc16::split16_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(B, ldb, N, K, (int)t.kp, vec, amax + 1, Bh, Bl);
   } else {
-    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + 63) / 64));
-    tc16::split16_transpose_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, amax + 1, Bh, Bl);
+    if (K >= 4096 && N >= 64) {  // long reduction (weight gradient): shared-memory-free form
+      dim3 grid((unsigned)((K + 15) / 16), (unsigned)((N + 255) / 256));
+      tc16::split16_transpose_direct_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, amax + 1, Bh, Bl);
+    } else {
+      dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + 63) / 64));
+      tc16::split16_transpose_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, amax + 1, Bh, Bl);
+    }
   }
-  GOTEN_CHECK_LAUNCH();
+  if (!t.b_raw) GOTEN_CHECK_LAUNCH();
 
   CUtensorMap mA, mBh, mBl, mC;
   bool ok;
   if (!t.a_rows_are_k) ok = make_map_f32(&mA, A, lda, M, K, 32, tc16::BM, CU_TENSOR_MAP_SWIZZLE_128B);
   else ok = make_map_f32(&mA, A, lda, K, M, tc16::BM, tc16::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
-  ok = ok && make_map_f16(&mBh, Bh, t.kp, N, K, t.block_n / t.ncta) && make_map_f16(&mBl, Bl, t.kp, N, K, t.block_n / t.ncta);
+  if (t.b_raw) {
+    ok = ok && make_map_f32(&mBh, B, ldb, K, N, t.block_n / t.ncta, tc16::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
+    mBl = mBh;
+  } else {
+    ok = ok && make_map_f16(&mBh, Bh, t.kp, N, K, t.block_n / t.ncta) && make_map_f16(&mBl, Bl, t.kp, N, K, t.block_n / t.ncta);
+  }
   GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed (fp16 GEMM M=%d N=%d K=%d lda=%d)", M, N, K, lda);
   const bool fast_epi = t.splits > 1 || ((add_src == nullptr) && (act_out == nullptr));
   if (t.splits > 1) ok = make_map_f32(&mC, partial, N, (int64_t)t.splits * M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -694,9 +769,9 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-#define GOTEN_TC16_LAUNCH(RK, NC)                                                                           \
+#define GOTEN_TC16_LAUNCH(RK, BR, NC)                                                                          \
   do {                                                                                                      \
-    auto k = tc16::gemm16_kernel<RK, NC>;                                                                   \
+    auto k = tc16::gemm16_kernel<RK, BR, NC>;                                                                 \
     static int smem_set = 0;                                                                                \
     if ((int)smem > smem_set) {                                                                             \
       GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));   \
@@ -704,10 +779,12 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     }                                                                                                       \
     GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, p));                                     \
   } while (0)
-  if (t.a_rows_are_k) {
-    if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, 2); else GOTEN_TC16_LAUNCH(true, 1);
+  if (t.b_raw) {
+    if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, true, 2); else GOTEN_TC16_LAUNCH(true, true, 1);
+  } else if (t.a_rows_are_k) {
+    if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, false, 2); else GOTEN_TC16_LAUNCH(true, false, 1);
   } else {
-    if (t.ncta == 2) GOTEN_TC16_LAUNCH(false, 2); else GOTEN_TC16_LAUNCH(false, 1);
+    if (t.ncta == 2) GOTEN_TC16_LAUNCH(false, false, 2); else GOTEN_TC16_LAUNCH(false, false, 1);
   }
 #undef GOTEN_TC16_LAUNCH
   GOTEN_CHECK_LAUNCH();

@@ -15,62 +15,91 @@ namespace goten {
 
 constexpr int HTR_SEP = 1, HTR_REJ = 2;
 
-// accumulate  sum_m (q_m - a y_m)(k_m - b y_m)  over one group [lo,hi)
+// Rejection algebra.  With P = I - y y^T applied per group (degree l if sep_htr, else all of L):
+//   (P q).(P k) = q.k - (q.y)(k.y) n,      n = 2 - |y|^2     (n = 0 switches the rejection off)
+//   d/dq [(P q).(P k)] = k - n (k.y) y     (symmetric in q <-> k)
+// n depends on the edge only, so the per-channel work is three dot products (forward) plus two FMAs per
+// component (gradient) instead of forming both rejected vectors.
 template <int LO, int HI>
-__device__ __forceinline__ float group_weight(const float* q, const float* k, const float* y, bool rej) {
-  float w = 0.f;
-  if (rej) {
-    float a = 0.f, b = 0.f;
+__device__ __forceinline__ float group_n(const float* y, bool rej) {
+  if (!rej) return 0.f;
+  float s = 0.f;
 #pragma unroll
-    for (int m = LO; m < HI; ++m) { a = fmaf(q[m], y[m], a); b = fmaf(k[m], y[m], b); }
+  for (int m = LO; m < HI; ++m) s = fmaf(y[m], y[m], s);
+  return 2.0f - s;
+}
+// n[g] for the (up to three) groups of one edge
+template <int LMAX>
+__device__ __forceinline__ void htr_coef(const float* y, int flags, float* n) {
+  constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
+  const bool rej = flags & HTR_REJ;
+  n[0] = n[1] = n[2] = 0.f;
+  if (!(flags & HTR_SEP)) { n[0] = group_n<0, L>(y, rej); return; }
+  n[0] = group_n<0, 3>(y, rej);
+  if (LMAX >= 2) n[1] = group_n<3, 8>(y, rej);
+  if (LMAX >= 3) n[2] = group_n<8, 15>(y, rej);
+}
+
+template <int LO, int HI>
+__device__ __forceinline__ float group_weight(const float* q, const float* k, const float* y, float n) {
+  float a = 0.f, b = 0.f, s = 0.f;
 #pragma unroll
-    for (int m = LO; m < HI; ++m) w = fmaf(q[m] - a * y[m], k[m] - b * y[m], w);
-  } else {
-#pragma unroll
-    for (int m = LO; m < HI; ++m) w = fmaf(q[m], k[m], w);
-  }
-  return w;
+  for (int m = LO; m < HI; ++m) { a = fmaf(q[m], y[m], a); b = fmaf(k[m], y[m], b); s = fmaf(q[m], k[m], s); }
+  return fmaf(-n * a, b, s);
 }
 
 template <int LMAX>
-__device__ __forceinline__ float htr_weight(const float* q, const float* k, const float* y, int flags) {
+__device__ __forceinline__ float htr_weight(const float* q, const float* k, const float* y, const float* n, int flags) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
-  const bool rej = flags & HTR_REJ;
-  if (!(flags & HTR_SEP)) return group_weight<0, L>(q, k, y, rej);
-  float w = group_weight<0, 3>(q, k, y, rej);
-  if (LMAX >= 2) w += group_weight<3, 8>(q, k, y, rej);
-  if (LMAX >= 3) w += group_weight<8, 15>(q, k, y, rej);
+  if (!(flags & HTR_SEP)) return group_weight<0, L>(q, k, y, n[0]);
+  float w = group_weight<0, 3>(q, k, y, n[0]);
+  if (LMAX >= 2) w += group_weight<3, 8>(q, k, y, n[1]);
+  if (LMAX >= 3) w += group_weight<8, 15>(q, k, y, n[2]);
   return w;
 }
 
-// gradient of one group w.r.t. `q` given the other operand `k`:  out_m += dw * P (k - b y)_m with
-// P = I - y y^T (rejection on) or out_m += dw * k_m (off).  Symmetric in q <-> k.
+// out_m += dw * (k_m - n (k.y) y_m): gradient of one group w.r.t. `q` given the other operand `k`
 template <int LO, int HI>
-__device__ __forceinline__ void group_grad(const float* k, const float* y, bool rej, float dw, float* out) {
-  if (rej) {
-    float b = 0.f;
+__device__ __forceinline__ void group_grad(const float* k, const float* y, float n, float dw, float* out) {
+  float b = 0.f;
 #pragma unroll
-    for (int m = LO; m < HI; ++m) b = fmaf(k[m], y[m], b);
-    float kt[HI - LO];
-    float s = 0.f;
+  for (int m = LO; m < HI; ++m) b = fmaf(k[m], y[m], b);
+  const float cy = -dw * n * b;
 #pragma unroll
-    for (int m = LO; m < HI; ++m) { kt[m - LO] = dw * (k[m] - b * y[m]); s = fmaf(kt[m - LO], y[m], s); }
-#pragma unroll
-    for (int m = LO; m < HI; ++m) out[m] += kt[m - LO] - s * y[m];
-  } else {
-#pragma unroll
-    for (int m = LO; m < HI; ++m) out[m] = fmaf(dw, k[m], out[m]);
-  }
+  for (int m = LO; m < HI; ++m) out[m] = fmaf(dw, k[m], fmaf(cy, y[m], out[m]));
 }
 
 template <int LMAX>
-__device__ __forceinline__ void htr_grad(const float* k, const float* y, int flags, float dw, float* out) {
+__device__ __forceinline__ void htr_grad(const float* k, const float* y, const float* n, int flags, float dw, float* out) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
-  const bool rej = flags & HTR_REJ;
-  if (!(flags & HTR_SEP)) { group_grad<0, L>(k, y, rej, dw, out); return; }
-  group_grad<0, 3>(k, y, rej, dw, out);
-  if (LMAX >= 2) group_grad<3, 8>(k, y, rej, dw, out);
-  if (LMAX >= 3) group_grad<8, 15>(k, y, rej, dw, out);
+  if (!(flags & HTR_SEP)) { group_grad<0, L>(k, y, n[0], dw, out); return; }
+  group_grad<0, 3>(k, y, n[0], dw, out);
+  if (LMAX >= 2) group_grad<3, 8>(k, y, n[1], dw, out);
+  if (LMAX >= 3) group_grad<8, 15>(k, y, n[2], dw, out);
+}
+
+// weight and gradient w.r.t. q in one pass (target half of the backward): returns the group's weight
+template <int LO, int HI>
+__device__ __forceinline__ float group_weight_grad(const float* q, const float* k, const float* y, float n, float dw,
+                                                   float* out) {
+  float a = 0.f, b = 0.f, s = 0.f;
+#pragma unroll
+  for (int m = LO; m < HI; ++m) { a = fmaf(q[m], y[m], a); b = fmaf(k[m], y[m], b); s = fmaf(q[m], k[m], s); }
+  const float nb = n * b, cy = -dw * nb;
+#pragma unroll
+  for (int m = LO; m < HI; ++m) out[m] = fmaf(dw, k[m], fmaf(cy, y[m], out[m]));
+  return fmaf(-nb, a, s);
+}
+
+template <int LMAX>
+__device__ __forceinline__ float htr_weight_grad(const float* q, const float* k, const float* y, const float* n, int flags,
+                                                 float dw, float* out) {
+  constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
+  if (!(flags & HTR_SEP)) return group_weight_grad<0, L>(q, k, y, n[0], dw, out);
+  float w = group_weight_grad<0, 3>(q, k, y, n[0], dw, out);
+  if (LMAX >= 2) w += group_weight_grad<3, 8>(q, k, y, n[1], dw, out);
+  if (LMAX >= 3) w += group_weight_grad<8, 15>(q, k, y, n[2], dw, out);
+  return w;
 }
 
 // d w / d y_m for one group (rejection on): w = sum (q - a y)(k - b y), a = q.y, b = k.y
@@ -93,6 +122,9 @@ __device__ __forceinline__ void ldv(const float* __restrict__ p, float* out) {
   if (V == 4) {
     const float4 t = *reinterpret_cast<const float4*>(p);
     out[0] = t.x; out[1] = t.y; out[2] = t.z; out[3] = t.w;
+  } else if (V == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(p);
+    out[0] = t.x; out[1] = t.y;
   } else {
 #pragma unroll
     for (int q = 0; q < V; ++q) out[q] = p[q];
@@ -102,6 +134,8 @@ template <int V>
 __device__ __forceinline__ void stv(float* __restrict__ p, const float* in) {
   if (V == 4) {
     *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+  } else if (V == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(in[0], in[1]);
   } else {
 #pragma unroll
     for (int q = 0; q < V; ++q) p[q] = in[q];
@@ -132,19 +166,22 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
     for (int m = 0; m < L; ++m) { ldv<V>(EK + ((size_t)m * N + j) * C + c, k[m]); y[m] = Y[(size_t)e * L + m]; }
     ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
     ldv<V>(t + (size_t)e * C + c, tv);
+    float nn[3];
+    htr_coef<LMAX>(y, flags, nn);
 #pragma unroll
     for (int qq = 0; qq < V; ++qq) {
       float qc[L], kc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(k, qq, kc);
-      tv[qq] = fmaf(siluf_(zt[qq]), htr_weight<LMAX>(qc, kc, y, flags), tv[qq]);
+      tv[qq] = fmaf(siluf_(zt[qq]), htr_weight<LMAX>(qc, kc, y, nn, flags), tv[qq]);
     }
     stv<V>(t_out + (size_t)e * C + c, tv);
   }
 }
 
-template <int LMAX, int V>
-__global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
+// GY: also produce the geometry gradient g_Y (forces); kept out of the common instantiation (registers)
+template <int LMAX, int V, bool GY>
+__device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
                                    const float* __restrict__ EK, const float* __restrict__ Y,
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
                                    const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
@@ -173,20 +210,22 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
       for (int m = 0; m < L; ++m) ldv<V>(EK + ((size_t)m * N + j) * C + c, k[m]);
       ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
       ldv<V>(g_t_out + (size_t)e * C + c, dt);
+      float nn[3];
+      htr_coef<LMAX>(y, flags, nn);
 #pragma unroll
       for (int qq = 0; qq < V; ++qq) {
         float qc[L], kc[L], gc[L];
         col_of<L, V>(q, qq, qc);
         col_of<L, V>(k, qq, kc);
         col_of<L, V>(gq, qq, gc);
-        const float w = htr_weight<LMAX>(qc, kc, y, flags);
-        gz[qq] = dt[qq] * w * dsiluf_(zt[qq]);
+        const float sg = sigmoidf_(zt[qq]);
+        const float dw = dt[qq] * zt[qq] * sg;                 // dt * silu(zt)
+        const float w = htr_weight_grad<LMAX>(qc, kc, y, nn, flags, dw, gc);
+        gz[qq] = dt[qq] * w * sg * (1.0f + zt[qq] * (1.0f - sg));  // dt * w * silu'(zt)
         amx = fmaxf(amx, fabsf(gz[qq]));
-        const float dw = dt[qq] * siluf_(zt[qq]);
-        htr_grad<LMAX>(kc, y, flags, dw, gc);
 #pragma unroll
         for (int m = 0; m < L; ++m) gq[m][qq] = gc[m];
-        if (g_Y != nullptr && (flags & HTR_REJ)) {
+        if (GY && (flags & HTR_REJ)) {
           float g1[L];
 #pragma unroll
           for (int m = 0; m < L; ++m) g1[m] = 0.f;
@@ -202,7 +241,7 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
       }
       stv<V>(gZe + (size_t)e * ldgz + zt_col0 + c, gz);
     }
-    if (g_Y != nullptr) {  // block-uniform: geometry gradient for forces
+    if (GY) {  // geometry gradient for forces
 #pragma unroll
       for (int m = 0; m < L; ++m) {
         const float s = block_sum(gy[m], red);
@@ -215,6 +254,27 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
     for (int m = 0; m < L; ++m) stv<V>(g_EQ + ((size_t)m * N + i) * C + c, gq[m]);
   }
   amax_commit(gze_amax, amx);
+}
+
+template <int LMAX, int V>
+__global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
+                                   const float* __restrict__ EK, const float* __restrict__ Y,
+                                   const float* __restrict__ Ze, int ldz, int zt_col0,
+                                   const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
+                                   int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
+                                   float* __restrict__ g_Y, float* __restrict__ gze_amax) {
+  htr_bwd_tgt_body<LMAX, V, false>(g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
+                                   gze_amax);
+}
+template <int LMAX, int V>
+__global__ void htr_bwd_tgt_gy_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
+                                      const float* __restrict__ EK, const float* __restrict__ Y,
+                                      const float* __restrict__ Ze, int ldz, int zt_col0,
+                                      const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N,
+                                      int C, int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
+                                      float* __restrict__ g_Y, float* __restrict__ gze_amax) {
+  htr_bwd_tgt_body<LMAX, V, true>(g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
+                                  gze_amax);
 }
 
 template <int LMAX, int V>
@@ -240,12 +300,14 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
     for (int m = 0; m < L; ++m) { ldv<V>(EQ + ((size_t)m * N + i) * C + c, q[m]); y[m] = Y[(size_t)e * L + m]; }
     ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
     ldv<V>(g_t_out + (size_t)e * C + c, dt);
+    float nn[3];
+    htr_coef<LMAX>(y, flags, nn);
 #pragma unroll
     for (int qq = 0; qq < V; ++qq) {
       float qc[L], gc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(gk, qq, gc);
-      htr_grad<LMAX>(qc, y, flags, dt[qq] * siluf_(zt[qq]), gc);  // d w / d k = P (q - a y) dw : q <-> k symmetric
+      htr_grad<LMAX>(qc, y, nn, flags, dt[qq] * siluf_(zt[qq]), gc);  // d w / d k: q <-> k symmetric
 #pragma unroll
       for (int m = 0; m < L; ++m) gk[m][qq] = gc[m];
     }
@@ -255,6 +317,12 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
 }
 
 static inline int block_for(int C, int V) { return (((C + V - 1) / V + 31) / 32) * 32; }
+// channels per thread of the vector kernels: GOTEN_HTR_V=2|4 (A/B timing)
+static inline int htr_vec() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GOTEN_HTR_V"); v = (e && atoi(e) == 2) ? 2 : 4; }
+  return v;
+}
 
 }  // namespace goten
 
@@ -266,7 +334,13 @@ using namespace goten;
     GOTEN_REQUIRE(C >= 1 && C <= 4096, "n_atom_basis=%d unsupported (<=4096)", C);             \
     if (N == 0) return 0;                                                                      \
     cudaStream_t st = as_stream(stream);                                                       \
-    if (V4OK) {                                                                                \
+    if ((V4OK) && htr_vec() == 2) {                                                            \
+      const int T = block_for(C, 2);                                                           \
+      GOTEN_REQUIRE(T <= 1024, "n_atom_basis=%d too wide for the 2-channel HTR kernels", C);   \
+      if (lmax == 1) KERNEL<1, 2><<<N, T, 0, st>>>(__VA_ARGS__);                               \
+      else if (lmax == 2) KERNEL<2, 2><<<N, T, 0, st>>>(__VA_ARGS__);                          \
+      else KERNEL<3, 2><<<N, T, 0, st>>>(__VA_ARGS__);                                         \
+    } else if (V4OK) {                                                                         \
       const int T = block_for(C, 4);                                                           \
       if (lmax == 1) KERNEL<1, 4><<<N, T, 0, st>>>(__VA_ARGS__);                               \
       else if (lmax == 2) KERNEL<2, 4><<<N, T, 0, st>>>(__VA_ARGS__);                          \
@@ -293,6 +367,9 @@ int goten_htr_fwd(const float* EQ, const float* EK, const float* Y, const float*
 int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
                       float* g_EQ, float* gZe, int ldgz, float* g_Y, float* gze_amax, void* stream) {
+  if (g_Y != nullptr)
+    HTR_DISPATCH(htr_bwd_tgt_gy_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
+                 g_Y, gze_amax);
   HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
                g_Y, gze_amax);
 }

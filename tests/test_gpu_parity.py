@@ -94,6 +94,8 @@ def test_radius_graph_edge_cases(g, dev):
 def test_gemm_layouts(g, dev, M, N, K, impl):
     if impl in (2, 3) and N < 16:
         pytest.skip("tensor-core arms need N >= 16 (auto falls through to the SIMT arm)")
+    if impl == 3 and K % 4:
+        pytest.skip("TMA needs 16-byte aligned operand rows (auto falls through to the SIMT arm)")
     if impl == 2 and (M % 32 or N % 32 or K % 32):
         pytest.skip("the 3xTF32 arm rejects the unaligned weight-gradient form")
     from gotennet_b200 import ops

@@ -7,3 +7,5 @@ for k in d.get("kernels", []):
     print(f"  {k['entry']:30s} {k['launches_per_step']:4d}x {k['ms_per_step']:7.3f} ms {100 * k['share_of_step']:5.1f}%  frac {k.get('frac', 0):.3f} {extra}")
 r = d.get("roofline", {})
 print("roofline:", r.get("kernel"), f"achieved {r.get('achieved', 0):.1f} {r.get('unit')} frac {r.get('frac', 0):.3f}")
+for g in r.get("gemm_shapes", []):
+    print(f"  gemm M={g['M']:7d} N={g['N']:5d} K={g['K']:7d} t={g['trans']} {g['launches_per_step']:3d}x {g['ms_per_step']:7.3f} ms {g['tflops']:6.1f} TF/s")
