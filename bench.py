@@ -105,12 +105,17 @@ def kernel_report(prof, n_steps, N, E, peaks, ms_step):
         "goten_htr_bwd_tgt": 3 * E * C * f + 3 * L_ * node + E * L_ * f,
         "goten_htr_bwd_src": 2 * E * C * f + 2 * L_ * node + E * L_ * f,
     }
-    agg, gemm_shapes = {}, {}
+    agg, gemm_shapes, absmax_sizes = {}, {}, {}
     for name, a, e0, e1 in prof:
         ms = e0.elapsed_time(e1)
         d = agg.setdefault(name, [0, 0.0])
         d[0] += 1
         d[1] += ms
+        if name == "goten_absmax":
+            key = int(a[2]) * int(a[3])
+            g = absmax_sizes.setdefault(key, [0, 0.0])
+            g[0] += 1
+            g[1] += ms
         if name == "goten_gemm_scaled":
             key = (int(a[8]), int(a[9]), int(a[10]), int(a[2]), int(a[5]))  # M, N, K, trans_a, trans_b
             g = gemm_shapes.setdefault(key, [0, 0.0])
@@ -165,6 +170,8 @@ def kernel_report(prof, n_steps, N, E, peaks, ms_step):
                "ms_per_step": ms_ / n_steps, "tflops": 2.0 * k[0] * k[1] * k[2] * c / (ms_ * 1e-3) / 1e12}
               for k, (c, ms_) in sorted(gemm_shapes.items(), key=lambda kv: -kv[1][1])[:14]]
     roofline["gemm_shapes"] = shapes
+    roofline["absmax_passes"] = [{"elements": k, "launches_per_step": c // n_steps, "ms_per_step": ms_ / n_steps}
+                                 for k, (c, ms_) in sorted(absmax_sizes.items(), key=lambda kv: -kv[1][1])[:10]]
     return roofline, kernels
 
 # -------------------------------------------------------------- our arm -------

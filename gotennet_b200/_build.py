@@ -27,7 +27,8 @@ NVCC_FLAGS = [
 
 
 def lib_path() -> str:
-    return os.path.join(LIBDIR, LIBNAME)
+    # GOTEN_LIB_PATH: load another build of the same ABI (A/B timing of two kernel versions on one box)
+    return os.environ.get("GOTEN_LIB_PATH") or os.path.join(LIBDIR, LIBNAME)
 
 
 def _nvcc() -> str:

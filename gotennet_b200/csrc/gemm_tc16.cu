@@ -85,7 +85,7 @@ struct Params {
   const float* bias;
   const float* add_src; int ld_add;
   float* act_out; int ld_act, act_lo, act_hi;
-  int add_vec, c_vec;
+  int add_vec, c_vec, act_vec;
   float* partial;
   float* colsum;
   float* partial_colsum;
@@ -410,7 +410,12 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 if (n + 2 < p.N) cp[2] = v.z;
                 if (n + 3 < p.N) cp[3] = v.w;
               }
-              if (p.act_out) {
+              if (p.act_out && p.act_vec && n >= p.act_lo && n + 3 < p.act_hi) {  // whole float4 inside the SiLU range
+                float4 a;
+                a.x = __fdividef(v.x, 1.0f + __expf(-v.x)); a.y = __fdividef(v.y, 1.0f + __expf(-v.y));
+                a.z = __fdividef(v.z, 1.0f + __expf(-v.z)); a.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+                *reinterpret_cast<float4*>(p.act_out + (size_t)m * p.ld_act + (n - p.act_lo)) = a;
+              } else if (p.act_out) {
                 const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                 for (int qd = 0; qd < 4; ++qd) {
@@ -444,17 +449,35 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 }
 
 // ---------------------------------------------------------------- operand preparation
-// max |x| over a [rows][cols] matrix with leading dimension ld -> atomicMax on the (non-negative) float bits
-__global__ void absmax_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols, int vec, float* __restrict__ out) {
+// max |x| over a [rows][cols] matrix with leading dimension ld -> atomicMax on the (non-negative) float bits.
+// Vector form: four independent 128-bit loads per thread and iteration (a pure read stream: memory-level parallelism
+// is all that matters), one atomic per block.
+__global__ void __launch_bounds__(256) absmax_kernel(const float* __restrict__ in, int64_t ld, int64_t rows, int cols,
+                                                     int vec, float* __restrict__ out) {
+  __shared__ float red[8];
   float m = 0.f;
   if (vec) {
     const int c4 = cols >> 2;
     const int64_t total = rows * c4;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-      const int64_t r = idx / c4;
-      const int c = (int)(idx - r * c4);
-      const float4 v = *reinterpret_cast<const float4*>(in + r * ld + 4 * c);
-      m = fmaxf(m, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ld == cols) {  // contiguous: no row arithmetic
+      const float4* p = reinterpret_cast<const float4*>(in);
+      for (; idx + 3 * stride < total; idx += 4 * stride) {
+        const float4 a = p[idx], b = p[idx + stride], c = p[idx + 2 * stride], d = p[idx + 3 * stride];
+        m = amax4(amax4(amax4(amax4(m, a.x, a.y, a.z, a.w), b.x, b.y, b.z, b.w), c.x, c.y, c.z, c.w), d.x, d.y, d.z, d.w);
+      }
+      for (; idx < total; idx += stride) {
+        const float4 a = p[idx];
+        m = amax4(m, a.x, a.y, a.z, a.w);
+      }
+    } else {
+      for (; idx < total; idx += stride) {
+        const int64_t r = idx / c4;
+        const int c = (int)(idx - r * c4);
+        const float4 v = *reinterpret_cast<const float4*>(in + r * ld + 4 * c);
+        m = amax4(m, v.x, v.y, v.z, v.w);
+      }
     }
   } else {
     const int64_t total = rows * cols;
@@ -464,7 +487,13 @@ __global__ void absmax_kernel(const float* __restrict__ in, int64_t ld, int64_t 
     }
   }
   m = warp_max(m);
-  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(m));
+  }
 }
 
 // B[N][K] (ld) -> fp16 hi / lo [N][Kp]: thread = 4 consecutive k
@@ -643,7 +672,7 @@ static int launch_absmax(const float* P, int64_t ld, int64_t rows, int cols, flo
   const int vec = (cols % 4 == 0 && ld % 4 == 0 && aligned16(P)) ? 1 : 0;
   const int64_t work = vec ? rows * (cols / 4) : rows * cols;
   int64_t grid = cdiv64(work, 256 * 4);
-  if (grid > (int64_t)sm_count * 8) grid = (int64_t)sm_count * 8;
+  if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
   if (grid < 1) grid = 1;
   tc16::absmax_kernel<<<(unsigned)grid, 256, 0, st>>>(P, ld, rows, cols, vec, slot);
   GOTEN_CHECK_LAUNCH();
@@ -747,6 +776,7 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
   p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
   p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
+  p.act_vec = (act_out != nullptr && aligned16(act_out) && ld_act % 4 == 0 && act_lo % 4 == 0) ? 1 : 0;
   p.partial = partial; p.colsum = colsum; p.partial_colsum = partial_cs;
   p.amax = amax;
   if (t.splits > 1) { p.bias = nullptr; p.add_src = nullptr; p.act_out = nullptr; }

@@ -9,3 +9,5 @@ r = d.get("roofline", {})
 print("roofline:", r.get("kernel"), f"achieved {r.get('achieved', 0):.1f} {r.get('unit')} frac {r.get('frac', 0):.3f}")
 for g in r.get("gemm_shapes", []):
     print(f"  gemm M={g['M']:7d} N={g['N']:5d} K={g['K']:7d} t={g['trans']} {g['launches_per_step']:3d}x {g['ms_per_step']:7.3f} ms {g['tflops']:6.1f} TF/s")
+for g in r.get("absmax_passes", []):
+    print(f"  absmax {g['elements'] * 4 / 1e6:8.1f} MB {g['launches_per_step']:3d}x {g['ms_per_step']:7.3f} ms")
