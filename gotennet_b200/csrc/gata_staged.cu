@@ -249,6 +249,8 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
   float* part = s_Y + EC * L;                           // [max_deg][S][n_grp]
   float* s_al = part + (size_t)max_deg * S * n_grp;     // [max_deg][H]
   float* s_aux = s_al + (size_t)max_deg * H;            // [max_deg][H]
+  // [2][S][blockDim]: per-thread d alpha~ partials of one edge (16 B aligned for the vector group sums)
+  float* s_pk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_aux + (size_t)max_deg * H) + 15) & ~uintptr_t(15));
   const uint32_t bar0 = tma::smem_u32(bars);
   const uint32_t stage0 = tma::smem_u32(stages);
 
@@ -325,13 +327,29 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
           st4(gz + k * C, gv);
         }
       }
+      // group sums of the partials (gt_ consecutive threads, never across a warp): every thread stores its S values,
+      // then S * n_grp threads each add one group's gt_ values (conflict-free smem reads instead of S log2(gt_)
+      // dependent shuffles per thread)
+      // (double buffered on the edge parity: the buffer written for edge t is re-written for edge t + 2, which a
+      //  thread reaches only after the barrier of edge t + 1, i.e. after every thread has finished reading it)
+      float* pkb = s_pk + (size_t)(gt & 1) * S * blockDim.x;
 #pragma unroll
-      for (int k = 0; k < S; ++k) {
-        float p = pk[k];
-        for (int o = gt_ >> 1; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
-        if (act && (tid % gt_) == 0) part[((size_t)gt * S + k) * n_grp + tid / gt_] = p;
-      }
+      for (int k = 0; k < S; ++k) pkb[k * blockDim.x + tid] = pk[k];
       __syncthreads();
+      for (int o = tid; o < S * n_grp; o += blockDim.x) {
+        const int k = o / n_grp, g = o - k * n_grp;
+        const float* pp = pkb + k * blockDim.x + g * gt_;
+        float p = 0.f;
+        if ((gt_ & 3) == 0) {
+          for (int u = 0; u < gt_; u += 4) {
+            const float4 q4 = *reinterpret_cast<const float4*>(pp + u);
+            p += (q4.x + q4.y) + (q4.z + q4.w);
+          }
+        } else {
+          for (int u = 0; u < gt_; ++u) p += pp[u];
+        }
+        part[(size_t)gt * S * n_grp + o] = p;
+      }
       if (tid == 0 && t + R < n) issue(gt + R, t + R);
     }
   }
@@ -381,12 +399,16 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
     for (int u = 0; u < 4; ++u) {
       if (t0 + u < deg) {
         const float dal = s_aux[(t0 + u) * H + hq];
-        gq.x = fmaf(dal * kj[u].x, siluf_(zr[u].x), gq.x);
-        gq.y = fmaf(dal * kj[u].y, siluf_(zr[u].y), gq.y);
-        gq.z = fmaf(dal * kj[u].z, siluf_(zr[u].z), gq.z);
-        gq.w = fmaf(dal * kj[u].w, siluf_(zr[u].w), gq.w);
-        const float4 gv = make_float4(dal * qi.x * kj[u].x * dsiluf_(zr[u].x), dal * qi.y * kj[u].y * dsiluf_(zr[u].y),
-                                      dal * qi.z * kj[u].z * dsiluf_(zr[u].z), dal * qi.w * kj[u].w * dsiluf_(zr[u].w));
+        // one sigmoid per element serves silu (for dq) and silu' (for d pre-act W_re)
+        const float4 sg = make_float4(sigmoidf_(zr[u].x), sigmoidf_(zr[u].y), sigmoidf_(zr[u].z), sigmoidf_(zr[u].w));
+        gq.x = fmaf(dal * kj[u].x, zr[u].x * sg.x, gq.x);
+        gq.y = fmaf(dal * kj[u].y, zr[u].y * sg.y, gq.y);
+        gq.z = fmaf(dal * kj[u].z, zr[u].z * sg.z, gq.z);
+        gq.w = fmaf(dal * kj[u].w, zr[u].w * sg.w, gq.w);
+        const float4 gv = make_float4(dal * qi.x * kj[u].x * sg.x * (1.0f + zr[u].x * (1.0f - sg.x)),
+                                      dal * qi.y * kj[u].y * sg.y * (1.0f + zr[u].y * (1.0f - sg.y)),
+                                      dal * qi.z * kj[u].z * sg.z * (1.0f + zr[u].z * (1.0f - sg.z)),
+                                      dal * qi.w * kj[u].w * sg.w * (1.0f + zr[u].w * (1.0f - sg.w)));
         amx = amax4(amx, gv.x, gv.y, gv.z, gv.w);
         st4(gZe + (size_t)(e0 + t0 + u) * ldgz + c, gv);
       }
@@ -659,7 +681,8 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   if (max_deg_in < 1) max_deg_in = 1;
   int R = staged::ring_depth();
   const size_t stage_bytes = (size_t)(2 * S + L) * C * 4;
-  const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (2 + L) * 4 + (size_t)max_deg_in * (S * n_grp + 2 * H) * 4;
+  const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (2 + L) * 4 + (size_t)max_deg_in * (S * n_grp + 2 * H) * 4 +
+                      (size_t)2 * S * block * 4 + 16;
   while (R > 1 && R * stage_bytes + tail > 220 * 1024) --R;
   const size_t smem = R * stage_bytes + tail;
   if (R * stage_bytes + tail > 220 * 1024) return 0;
