@@ -38,6 +38,10 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 // ---------------------------------------------------------------- device math
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
 __device__ __forceinline__ float siluf_(float x) { return x * sigmoidf_(x); }
+// Fast forms for the BACKWARD kernels (gradient factors): ex2.approx + rcp.approx, relative error ~1e-6 for |x| < 10
+// (the forward kernels keep the exact forms above).  __expf(-x) -> inf for x < -88 and the quotient -> 0, as exact.
+__device__ __forceinline__ float sigmoid_fast_(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_fast_(float x) { return x * sigmoid_fast_(x); }
 // d/dx silu(x) = s + x s (1 - s)
 __device__ __forceinline__ float dsiluf_(float x) {
   float s = sigmoidf_(x);

@@ -400,7 +400,7 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
       if (t0 + u < deg) {
         const float dal = s_aux[(t0 + u) * H + hq];
         // one sigmoid per element serves silu (for dq) and silu' (for d pre-act W_re)
-        const float4 sg = make_float4(sigmoidf_(zr[u].x), sigmoidf_(zr[u].y), sigmoidf_(zr[u].z), sigmoidf_(zr[u].w));
+        const float4 sg = make_float4(sigmoid_fast_(zr[u].x), sigmoid_fast_(zr[u].y), sigmoid_fast_(zr[u].z), sigmoid_fast_(zr[u].w));
         gq.x = fmaf(dal * kj[u].x, zr[u].x * sg.x, gq.x);
         gq.y = fmaf(dal * kj[u].y, zr[u].y * sg.y, gq.y);
         gq.z = fmaf(dal * kj[u].z, zr[u].z * sg.z, gq.z);
@@ -553,8 +553,8 @@ __global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const 
         }
         const float4 qi = st[(S + 2 + L) * C4 + tid], zre = st[tid];
         const float dal = s_da[t * H + hq];
-        gk.x = fmaf(dal * qi.x, siluf_(zre.x), gk.x); gk.y = fmaf(dal * qi.y, siluf_(zre.y), gk.y);
-        gk.z = fmaf(dal * qi.z, siluf_(zre.z), gk.z); gk.w = fmaf(dal * qi.w, siluf_(zre.w), gk.w);
+        gk.x = fmaf(dal * qi.x, silu_fast_(zre.x), gk.x); gk.y = fmaf(dal * qi.y, silu_fast_(zre.y), gk.y);
+        gk.z = fmaf(dal * qi.z, silu_fast_(zre.z), gk.z); gk.w = fmaf(dal * qi.w, silu_fast_(zre.w), gk.w);
       }
       __syncthreads();
       if (tid == 0 && t + R < n) issue(gp + R, t + R);

@@ -259,7 +259,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
           col_of<L, V>(q, qq, qc);
           col_of<L, V>(k, qq, kc);
           col_of<L, V>(gq, qq, gc);
-          const float sg = sigmoidf_(zt[qq]);
+          const float sg = sigmoid_fast_(zt[qq]);
           const float dw = dt[qq] * zt[qq] * sg;                 // dt * silu(zt)
           const float w = htr_weight_grad<LMAX>(qc, kc, y, nn, flags, dw, gc);
           gz[qq] = dt[qq] * w * sg * (1.0f + zt[qq] * (1.0f - sg));  // dt * w * silu'(zt)
@@ -349,7 +349,7 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
       float qc[L], gc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(gk, qq, gc);
-      htr_grad<LMAX>(qc, y, nn, flags, dt[qq] * siluf_(zt[qq]), gc);  // d w / d k: q <-> k symmetric
+      htr_grad<LMAX>(qc, y, nn, flags, dt[qq] * silu_fast_(zt[qq]), gc);  // d w / d k: q <-> k symmetric
 #pragma unroll
       for (int m = 0; m < L; ++m) gk[m][qq] = gc[m];
     }
