@@ -89,7 +89,8 @@ struct Params {
   float* partial;
   float* colsum;
   float* partial_colsum;
-  const float* amax;      // [0] = max |A|, [1] = max |B| (device)
+  const float* amax_a;    // device scalars: (a bound of) max |A| and max |B|
+  const float* amax_b;
 };
 
 // B_RAW (weight-gradient form only): B is staged as raw fp32 [64 k][BNH n] like A and converted in place by the
@@ -221,8 +222,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp >= CONV_WARP0) {
     // =============================== converter ==================================
     const int ct = threadIdx.x - CONV_WARP0 * 32;  // 0..127 = tile row (M index) this thread produces
-    const float sA = scale_of(p.amax[0]);
-    const float sB = scale_of(p.amax[1]);
+    const float sA = scale_of(*p.amax_a);
+    const float sB = scale_of(*p.amax_b);
     const uint32_t sw = (uint32_t)(ct & 7);
     uint32_t it = 0;
     for (int w = unit; w < n_items; w += n_units) {
@@ -324,7 +325,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const int q = warp & 3;
     uint8_t* my_buf = epi_smem + (warp - EPI_WARP0) * 2 * 4096;
     const bool fast = (p.add_src == nullptr) && (p.act_out == nullptr);
-    const float un_a = inv_scale_of(p.amax[0]), un_b = inv_scale_of(p.amax[1]);
+    const float un_a = inv_scale_of(*p.amax_a), un_b = inv_scale_of(*p.amax_b);
     uint32_t tile_it = 0, n_store = 0;
     for (int w = unit; w < n_items; w += n_units, ++tile_it) {
       const int split = w / n_tiles, tile = w % n_tiles;
@@ -714,18 +715,19 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     partial_cs = partial + (size_t)t.splits * M * N;
   }
 
-  // ---- scales
-  if (a_amax && b_amax) {
-    GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax, a_amax, 4, cudaMemcpyDeviceToDevice, st));
-    GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax + 1, b_amax, 4, cudaMemcpyDeviceToDevice, st));
-  } else {
+  // ---- scales: caller-supplied bounds are read in place; missing ones are measured into the workspace slots
+  const float* pa = a_amax;
+  const float* pb = b_amax;
+  if (!pa || !pb) {
     GOTEN_CHECK_CUDA(cudaMemsetAsync(amax, 0, 8, st));
-    if (a_amax) GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax, a_amax, 4, cudaMemcpyDeviceToDevice, st));
-    else if (launch_absmax(A, lda, t.a_rows_are_k ? K : M, t.a_rows_are_k ? M : K, amax, sm_count, st)) return 1;
-    if (b_amax) GOTEN_CHECK_CUDA(cudaMemcpyAsync(amax + 1, b_amax, 4, cudaMemcpyDeviceToDevice, st));
-    else {
+    if (!pa) {
+      if (launch_absmax(A, lda, t.a_rows_are_k ? K : M, t.a_rows_are_k ? M : K, amax, sm_count, st)) return 1;
+      pa = amax;
+    }
+    if (!pb) {
       const bool b_is_nk = !t.a_rows_are_k && trans_b;   // B[N][K]; otherwise B[K][N]
       if (launch_absmax(B, ldb, b_is_nk ? N : K, b_is_nk ? K : N, amax + 1, sm_count, st)) return 1;
+      pb = amax + 1;
     }
   }
 
@@ -736,14 +738,14 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     const int64_t work = (int64_t)N * ((K + 3) / 4);
     int64_t grid = cdiv64(work, 256);
     if (grid > (int64_t)sm_count * 16) grid = (int64_t)sm_count * 16;
-    tc16::split16_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(B, ldb, N, K, (int)t.kp, vec, amax + 1, Bh, Bl);
+    tc16::split16_rows_kernel<<<(unsigned)grid, 256, 0, st>>>(B, ldb, N, K, (int)t.kp, vec, pb, Bh, Bl);
   } else {
     if (K >= 4096 && N >= 64) {  // long reduction (weight gradient): shared-memory-free form
       dim3 grid((unsigned)((K + 15) / 16), (unsigned)((N + 255) / 256));
-      tc16::split16_transpose_direct_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, amax + 1, Bh, Bl);
+      tc16::split16_transpose_direct_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, pb, Bh, Bl);
     } else {
       dim3 grid((unsigned)((N + 63) / 64), (unsigned)((K + 63) / 64));
-      tc16::split16_transpose_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, amax + 1, Bh, Bl);
+      tc16::split16_transpose_kernel<<<grid, 256, 0, st>>>(B, ldb, K, N, (int)t.kp, pb, Bh, Bl);
     }
   }
   if (!t.b_raw) GOTEN_CHECK_LAUNCH();
@@ -778,7 +780,7 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
   p.act_vec = (act_out != nullptr && aligned16(act_out) && ld_act % 4 == 0 && act_lo % 4 == 0) ? 1 : 0;
   p.partial = partial; p.colsum = colsum; p.partial_colsum = partial_cs;
-  p.amax = amax;
+  p.amax_a = pa; p.amax_b = pb;
   if (t.splits > 1) { p.bias = nullptr; p.add_src = nullptr; p.act_out = nullptr; }
 
   const size_t smem = 1024 + (size_t)t.stages * (tc16::A_BYTES + 2 * (size_t)(t.block_n / t.ncta) * tc16::BK * 2) +

@@ -103,6 +103,15 @@ class AmaxScope:
     def __init__(self):
         self.enabled = gemm_impl() in (0, 3) and os.environ.get("GOTEN_TC16", "1") != "0"
         self._d = {}
+        self._pool, self._used = None, 0
+
+    def slot(self, device):
+        """A zeroed 1-element device tensor (one fill kernel per 32 slots, not per tensor)."""
+        if self._pool is None or self._used == self._pool.numel() or self._pool.device != device:
+            self._pool, self._used = torch.zeros(32, device=device, dtype=torch.float32), 0
+        out = self._pool[self._used:self._used + 1]
+        self._used += 1
+        return out
 
     def put(self, T, a):
         if T is not None and a is not None:
@@ -112,7 +121,7 @@ class AmaxScope:
         ent = self._d.get(T.data_ptr())
         if ent is None:
             cols = T.shape[-1]
-            ent = (T, absmax(T, cols, T.numel() // max(cols, 1), cols))
+            ent = (T, absmax(T, cols, T.numel() // max(cols, 1), cols, out=self.slot(T.device)))
             self._d[T.data_ptr()] = ent
         return ent[1]
 
@@ -430,7 +439,7 @@ class GataBlockFn(torch.autograd.Function):
         if g_t1 is not None:
             g_t1 = g_t1.contiguous()
         gZe = torch.empty(E, ldz, device=dev)
-        gze_amax = torch.zeros(1, device=dev) if am.enabled else None  # written by the two kernels that fill gZe
+        gze_amax = am.slot(dev) if am.enabled else None  # written by the two kernels that fill gZe
         am.put(gZe, gze_amax)
         g_Y = torch.zeros(E, L, device=dev) if need_gY else None
         g_fc = torch.zeros(E, device=dev) if need_gfc else None
