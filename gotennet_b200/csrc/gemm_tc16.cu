@@ -656,7 +656,7 @@ static Tc16Plan tc16_plan(int M, int N, int K, int trans_a, int trans_b) {
   // it in place (no pre-split copy through HBM).  With several M tiles the kernel is shared-memory-bandwidth bound and
   // re-converting B per M tile costs more than the one pre-split pass (measured: 1792 x 256 x 301k, 0.94 -> 1.00 ms).
   // Needs one tile column per converter thread (BNH <= 128) and a TMA-addressable B (checked at launch).
-  t.b_raw = t.a_rows_are_k && t.n_mt == 1 && t.block_n / t.ncta <= 128;
+  t.b_raw = t.a_rows_are_k && t.n_mt <= 2 && t.block_n / t.ncta <= 128;
   t.b_bytes = align256((int64_t)N * t.kp * 2);
   t.ws_bytes = 256 + 2 * t.b_bytes;
   if (t.splits > 1) t.ws_bytes += align256((int64_t)t.splits * ((int64_t)M * N + M) * 4);

@@ -184,7 +184,7 @@ __device__ __forceinline__ void fill_meta(EdgeMeta<(LMAX + 1) * (LMAX + 1) - 1>&
 }
 
 template <int LMAX, int V>
-__global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __restrict__ EK, const float* __restrict__ Y,
+__global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                const float* __restrict__ Ze, int ldz, int zt_col0, const float* __restrict__ t,
                                const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
                                int flags, float* __restrict__ t_out) {
@@ -193,12 +193,12 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
   if (c >= C) return;
   float q[L][V];
 #pragma unroll
-  for (int m = 0; m < L; ++m) ldv<V>(EQ + ((size_t)m * N + i) * C + c, q[m]);
+  for (int m = 0; m < L; ++m) ldv<V>(EQ + ((size_t)m * N + i) * ldp + c, q[m]);
   for (int e = tgt_ptr[i]; e < tgt_ptr[i + 1]; ++e) {
     const int j = src[e];
     float k[L][V], y[L], zt[V], tv[V];
 #pragma unroll
-    for (int m = 0; m < L; ++m) { ldv<V>(EK + ((size_t)m * N + j) * C + c, k[m]); y[m] = Y[(size_t)e * L + m]; }
+    for (int m = 0; m < L; ++m) { ldv<V>(EK + ((size_t)m * N + j) * ldp + c, k[m]); y[m] = Y[(size_t)e * L + m]; }
     ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
     ldv<V>(t + (size_t)e * C + c, tv);
     float nn[3];
@@ -217,7 +217,7 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
 // GY: also produce the geometry gradient g_Y (forces); kept out of the common instantiation (registers)
 template <int LMAX, int V, bool GY>
 __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
-                                                 const float* __restrict__ EK, const float* __restrict__ Y,
+                                                 const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                                  const float* __restrict__ Ze, int ldz, int zt_col0,
                                                  const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src,
                                                  int N, int C, int flags, float* __restrict__ g_EQ,
@@ -234,7 +234,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
   for (int m = 0; m < L; ++m) {
 #pragma unroll
     for (int qq = 0; qq < V; ++qq) { q[m][qq] = 0.f; gq[m][qq] = 0.f; }
-    if (act) ldv<V>(EQ + ((size_t)m * N + i) * C + c, q[m]);
+    if (act) ldv<V>(EQ + ((size_t)m * N + i) * ldp + c, q[m]);
   }
   const int e_end = tgt_ptr[i + 1];
   for (int e0 = tgt_ptr[i]; e0 < e_end; e0 += EC) {
@@ -249,7 +249,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
       if (act) {
         float k[L][V], zt[V], dt[V], gz[V];
 #pragma unroll
-        for (int m = 0; m < L; ++m) ldv<V>(EK + ((size_t)m * N + j) * C + c, k[m]);
+        for (int m = 0; m < L; ++m) ldv<V>(EK + ((size_t)m * N + j) * ldp + c, k[m]);
         ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
         ldv<V>(g_t_out + (size_t)e * C + c, dt);
         const float nn[3] = {sm.n[u * 3], sm.n[u * 3 + 1], sm.n[u * 3 + 2]};
@@ -293,35 +293,35 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
   }
   if (act) {
 #pragma unroll
-    for (int m = 0; m < L; ++m) stv<V>(g_EQ + ((size_t)m * N + i) * C + c, gq[m]);
+    for (int m = 0; m < L; ++m) stv<V>(g_EQ + ((size_t)m * N + i) * ldp + c, gq[m]);
   }
   amax_commit(gze_amax, amx);
 }
 
 template <int LMAX, int V>
 __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
-                                   const float* __restrict__ EK, const float* __restrict__ Y,
+                                   const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
                                    const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
                                    int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
                                    float* __restrict__ g_Y, float* __restrict__ gze_amax) {
-  htr_bwd_tgt_body<LMAX, V, false>(g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
+  htr_bwd_tgt_body<LMAX, V, false>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
                                    gze_amax);
 }
 template <int LMAX, int V>
 __global__ void htr_bwd_tgt_gy_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
-                                      const float* __restrict__ EK, const float* __restrict__ Y,
+                                      const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                       const float* __restrict__ Ze, int ldz, int zt_col0,
                                       const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N,
                                       int C, int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
                                       float* __restrict__ g_Y, float* __restrict__ gze_amax) {
-  htr_bwd_tgt_body<LMAX, V, true>(g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
+  htr_bwd_tgt_body<LMAX, V, true>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
                                   gze_amax);
 }
 
 template <int LMAX, int V>
 __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
-                                   const float* __restrict__ EK, const float* __restrict__ Y,
+                                   const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
                                    const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src_perm,
                                    const int32_t* __restrict__ tgt, int N, int C, int flags,
@@ -339,7 +339,7 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
     const int i = tgt[e];
     float q[L][V], y[L], zt[V], dt[V];
 #pragma unroll
-    for (int m = 0; m < L; ++m) { ldv<V>(EQ + ((size_t)m * N + i) * C + c, q[m]); y[m] = Y[(size_t)e * L + m]; }
+    for (int m = 0; m < L; ++m) { ldv<V>(EQ + ((size_t)m * N + i) * ldp + c, q[m]); y[m] = Y[(size_t)e * L + m]; }
     ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
     ldv<V>(g_t_out + (size_t)e * C + c, dt);
     float nn[3];
@@ -355,7 +355,7 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
     }
   }
 #pragma unroll
-  for (int m = 0; m < L; ++m) stv<V>(g_EK + ((size_t)m * N + j) * C + c, gk[m]);
+  for (int m = 0; m < L; ++m) stv<V>(g_EK + ((size_t)m * N + j) * ldp + c, gk[m]);
 }
 
 static inline int block_for(int C, int V) { return (((C + V - 1) / V + 31) / 32) * 32; }
@@ -401,26 +401,26 @@ using namespace goten;
 
 extern "C" {
 
-int goten_htr_fwd(const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz, int zt_col0,
+int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz, int zt_col0,
                   const float* t, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
                   float* t_out, void* stream) {
-  HTR_DISPATCH(htr_fwd_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 4, EQ, EK, Y, Ze, ldz, zt_col0, t, tgt_ptr, src, N, C, flags, t_out);
+  HTR_DISPATCH(htr_fwd_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 4, EQ, EK, ldp, Y, Ze, ldz, zt_col0, t, tgt_ptr, src, N, C, flags, t_out);
 }
 
-int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
+int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
                       float* g_EQ, float* gZe, int ldgz, float* g_Y, float* gze_amax, void* stream) {
   if (g_Y != nullptr)
-    HTR_DISPATCH(htr_bwd_tgt_gy_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
+    HTR_DISPATCH(htr_bwd_tgt_gy_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
                  g_Y, gze_amax);
-  HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
+  HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
                g_Y, gze_amax);
 }
 
-int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
+int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* src_ptr, const int32_t* src_perm, const int32_t* tgt, int N, int C,
                       int lmax, int flags, float* g_EK, void* stream) {
-  HTR_DISPATCH(htr_bwd_src_kernel, (C % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 2, g_t_out, EQ, EK, Y, Ze, ldz, zt_col0, src_ptr, src_perm, tgt, N, C, flags, g_EK);
+  HTR_DISPATCH(htr_bwd_src_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 2, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, src_ptr, src_perm, tgt, N, C, flags, g_EK);
 }
 
 }  // extern "C"

@@ -395,23 +395,25 @@ class GataBlockFn(torch.autograd.Function):
         L_.call("goten_gata_fwd", _ptr(h), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze), ldz, _ptr(Y),
                 _ptr(fc), _ptr(kappa), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax, cfg["gata_flags"],
                 plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), st)
-        EQ = EK = None
+        EQK = Wqk = None
         t1 = t
         if htr:
-            EQ = torch.empty_like(Xd1)
-            EK = torch.empty_like(Xd1)
-            gemm(Xd1, C, 0, Wvq, C, 1, EQ, C, L * N, C, C, am=am)
+            # EQ = W_vq X and EK^l = W_vk,l X^l (gotennet.py:432-441) as ONE GEMM per degree group with the stacked
+            # weight [W_vq; W_vk,l]: rows of EQK are [EQ | EK] (pitch 2C), X is read once
+            G = len(cfg["vk_groups"])
+            Wqk = torch.cat([Wvq.unsqueeze(0).expand(G, C, C), Wvk], dim=1).contiguous()  # [G][2C][C]
+            EQK = torch.empty(L, N, 2 * C, device=dev)
             for g, (lo, hi) in enumerate(cfg["vk_groups"]):
                 rows = (hi - lo) * N
-                gemm(Xd1, C, 0, Wvk, C, 1, EK, C, rows, C, C, a_off=lo * N * C, b_off=g * C * C, c_off=lo * N * C, am=am)
+                gemm(Xd1, C, 0, Wqk, C, 1, EQK, 2 * C, rows, 2 * C, C, a_off=lo * N * C, b_off=g * 2 * C * C,
+                     c_off=lo * N * 2 * C, am=am)
             t1 = torch.empty_like(t)
-            L_.call("goten_htr_fwd", _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, (S + 1) * C, _ptr(t),
+            L_.call("goten_htr_fwd", _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, (S + 1) * C, _ptr(t),
                     _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(t1), st)
         ctx.plan, ctx.cfg, ctx.htr = plan, cfg, htr
-        amx = am.export([h, t, Wn1, Ws2, Wv2, We, Wvq, Wvk, A1, Xd1 if htr else None])
+        amx = am.export([h, t, Wn1, Ws2, Wv2, We, Wqk, A1, Xd1 if htr else None])
         ctx.n_amax = len(amx)
-        ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK,
-                              *amx)
+        ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wqk, Z1, A1, x, v, Ze, alpha, Xd1, EQK, *amx)
         if htr:
             return h1, Xd1, t1
         return h1, Xd1  # last layer: t_ij passes through unchanged (gotennet.py:449-450)
@@ -420,10 +422,10 @@ class GataBlockFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_h1, g_Xd1, g_t1=None):
         saved = ctx.saved_tensors
-        (h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wvq, Wvk, Z1, A1, x, v, Ze, alpha, Xd1, EQ, EK) = saved[:21]
+        (h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wqk, Z1, A1, x, v, Ze, alpha, Xd1, EQK) = saved[:19]
         plan, cfg, htr = ctx.plan, ctx.cfg, ctx.htr
         am = AmaxScope()
-        am.load([h, t, Wn1, Ws2, Wv2, We, Wvq, Wvk, A1, Xd1 if htr else None], saved[21:21 + ctx.n_amax])
+        am.load([h, t, Wn1, Ws2, Wv2, We, Wqk, A1, Xd1 if htr else None], saved[19:19 + ctx.n_amax])
         L_ = lib()
         st = _stream()
         N, C = h.shape
@@ -448,26 +450,27 @@ class GataBlockFn(torch.autograd.Function):
         if htr:
             if g_t1 is None:
                 g_t1 = torch.zeros(E, C, device=dev)
-            g_EQ = torch.empty_like(Xd1)
-            g_EK = torch.empty_like(Xd1)
+            g_EQK = torch.empty_like(EQK)  # rows [g_EQ | g_EK], pitch 2C
             zt0 = (S + 1) * C
-            L_.call("goten_htr_bwd_tgt", _ptr(g_t1), _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, zt0,
-                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(g_EQ), _ptr(gZe), ldz,
+            L_.call("goten_htr_bwd_tgt", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, zt0,
+                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(g_EQK), _ptr(gZe), ldz,
                     _ptr(g_Y), _ptr(gze_amax), st)
-            L_.call("goten_htr_bwd_src", _ptr(g_t1), _ptr(EQ), _ptr(EK), _ptr(Y), _ptr(Ze), ldz, zt0,
+            L_.call("goten_htr_bwd_src", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, zt0,
                     _ptr(plan.src_ptr), _ptr(plan.src_perm), _ptr(plan.tgt), N, C, lmax, cfg["htr_flags"],
-                    _ptr(g_EK), st)
-            # X gradient: g_Xm = g_Xd1 + g_EQ Wvq + g_EK^l Wvk_l ; weight gradients
+                    _ptr(g_EQK, C), st)
+            # X gradient: g_Xm^l = g_Xd1^l + [g_EQ | g_EK]^l [W_vq; W_vk,l] (one K = 2C GEMM per degree group, the
+            # residual added once); weight gradients of the stacked weight, un-stacked below
+            G = len(cfg["vk_groups"])
             g_Xm = torch.empty_like(Xd1)
-            gemm(g_EQ, C, 0, Wvq, C, 0, g_Xm, C, L * N, C, C, add_src=g_Xd1, ld_add=C, am=am)
-            dWvq = torch.empty_like(Wvq)
-            gemm(g_EQ, C, 1, Xd1, C, 0, dWvq, C, C, C, L * N, am=am)
-            dWvk = torch.empty_like(Wvk)
+            dWqk = torch.empty_like(Wqk)
             for g, (lo, hi) in enumerate(cfg["vk_groups"]):
                 rows, off = (hi - lo) * N, lo * N * C
-                gemm(g_EK, C, 0, Wvk, C, 0, g_Xm, C, rows, C, C, a_off=off, b_off=g * C * C, c_off=off,
-                     add_src=g_Xm, ld_add=C, add_off=off, am=am)
-                gemm(g_EK, C, 1, Xd1, C, 0, dWvk, C, C, C, rows, a_off=off, b_off=off, c_off=g * C * C, am=am)
+                gemm(g_EQK, 2 * C, 0, Wqk, C, 0, g_Xm, C, rows, C, 2 * C, a_off=2 * off, b_off=g * 2 * C * C, c_off=off,
+                     add_src=g_Xd1, ld_add=C, add_off=off, am=am)
+                gemm(g_EQK, 2 * C, 1, Xd1, C, 0, dWqk, C, 2 * C, C, rows, a_off=2 * off, b_off=off,
+                     c_off=g * 2 * C * C, am=am)
+            dWvq = dWqk[:, :C].sum(0) if G > 1 else dWqk[0, :C].contiguous()
+            dWvk = dWqk[:, C:].contiguous()
         # message block
         g_Z1 = torch.empty(N, 4 * C, device=dev)
         da = torch.empty(E, H, device=dev)

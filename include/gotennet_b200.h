@@ -208,18 +208,20 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
  * GATA.edge_update + vector_rejection + residual (gotennet.py:351-364, :561-611,
  * :445): EQ/EK are [L][N][C] projections of the post-message X;
  *   w[e][c] = sum_l sum_m rej(EQ_i)^l_m rej(EK_j)^l_m ;  t_out = t + silu(zt) * w
- * zt = Ze[:, zt_col0 : zt_col0+C).  flags: bit0 = sep_htr (rejection per degree),
+ * zt = Ze[:, zt_col0 : zt_col0+C).  EQ / EK / g_EQ / g_EK rows have pitch ldp floats
+ * (ldp = 2C with EK = EQ + C when both projections come from one GEMM with the stacked
+ * weight [W_vq; W_vk]).  flags: bit0 = sep_htr (rejection per degree),
  * bit1 = rejection enabled.                                                    */
-int goten_htr_fwd(const float* EQ, const float* EK, const float* Y, const float* Ze, int ldz,
+int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                   int zt_col0, const float* t, const int32_t* tgt_ptr, const int32_t* src,
                   int n_nodes, int C, int lmax, int flags, float* t_out, void* stream);
 /* target half: g_EQ[L][N][C], gZe[:, zt_col0..) = g_t_out * w * silu'(zt); optional g_Y (accumulated) */
-int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, const float* Y,
+int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y,
                       const float* Ze, int ldz, int zt_col0, const int32_t* tgt_ptr,
                       const int32_t* src, int n_nodes, int C, int lmax, int flags, float* g_EQ,
                       float* gZe, int ldgz, float* g_Y, float* gze_amax, void* stream);
 /* source half: g_EK[L][N][C] */
-int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, const float* Y,
+int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y,
                       const float* Ze, int ldz, int zt_col0, const int32_t* src_ptr,
                       const int32_t* src_perm, const int32_t* tgt, int n_nodes, int C, int lmax,
                       int flags, float* g_EK, void* stream);
