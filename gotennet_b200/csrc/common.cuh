@@ -81,6 +81,21 @@ __device__ __forceinline__ void amax_commit(float* out, float amx) {
   if (out != nullptr && amx > __ldcg(out)) atomicMax(reinterpret_cast<unsigned int*>(out), __float_as_uint(amx));
 }
 
+// Block-wide form (one request per block): every thread of the block must call it.
+__device__ __forceinline__ void block_amax_commit(float* out, float amx) {
+  if (out == nullptr) return;  // block-uniform
+  __shared__ float s_amax_red[32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  amx = warp_max(amx);
+  if (lane == 0) s_amax_red[w] = amx;
+  __syncthreads();
+  if (w == 0) {
+    float v = lane < nw ? s_amax_red[lane] : 0.f;
+    v = warp_max(v);
+    if (lane == 0) amax_commit(out, v);
+  }
+}
+
 // degree-l block boundaries inside the L axis: l = 1..lmax occupies [l^2-1, (l+1)^2-1)
 __host__ __device__ __forceinline__ constexpr int blk_lo(int l) { return l * l - 1; }            // l >= 1
 __host__ __device__ __forceinline__ constexpr int blk_hi(int l) { return (l + 1) * (l + 1) - 1; }

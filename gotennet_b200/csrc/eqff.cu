@@ -99,9 +99,10 @@ template <int V>
 __global__ void eqff_ctx_bwd_kernel(const float* __restrict__ g_h_out, const float* __restrict__ g_Xd_out,
                                     const float* __restrict__ g_ctx, const float* __restrict__ P,
                                     const float* __restrict__ mm, const float* __restrict__ ctx, int N, int C, int L,
-                                    float* __restrict__ g_P, float* __restrict__ g_h) {
+                                    float* __restrict__ g_P, float* __restrict__ g_h, float* __restrict__ gp_amax) {
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-  if (idx >= (int64_t)N * C) return;
+  float amx = 0.f;
+  if (idx < (int64_t)N * C) {
   const int64_t n = idx / C;
   const int c = (int)(idx % C);
   float gh[V], gc[V], m2[V], gn[V], nn[V];
@@ -121,9 +122,11 @@ __global__ void eqff_ctx_bwd_kernel(const float* __restrict__ g_h_out, const flo
     ldv<V>(g_Xd_out + o, gx);
     ldv<V>(P + o, p);
 #pragma unroll
-    for (int q = 0; q < V; ++q) gx[q] = fmaf(gx[q], m2[q], gn[q] * p[q]);
+    for (int q = 0; q < V; ++q) { gx[q] = fmaf(gx[q], m2[q], gn[q] * p[q]); amx = fmaxf(amx, fabsf(gx[q])); }
     stv<V>(g_P + o, gx);
   }
+  }
+  block_amax_commit(gp_amax, amx);
 }
 
 }  // namespace goten
@@ -161,9 +164,10 @@ int goten_eqff_update_bwd(const float* g_h_out, const float* g_Xd_out, const flo
   return 0;
 }
 int goten_eqff_ctx_bwd(const float* g_h_out, const float* g_Xd_out, const float* g_ctx, const float* P,
-                       const float* m, const float* ctx, int N, int C, int L, float* g_P, float* g_h, void* stream) {
+                       const float* m, const float* ctx, int N, int C, int L, float* g_P, float* g_h, float* gp_amax,
+                       void* stream) {
   if ((int64_t)N * C == 0) return 0;
-  EQFF_LAUNCH(eqff_ctx_bwd_kernel, N, C, g_h_out, g_Xd_out, g_ctx, P, m, ctx, N, C, L, g_P, g_h);
+  EQFF_LAUNCH(eqff_ctx_bwd_kernel, N, C, g_h_out, g_Xd_out, g_ctx, P, m, ctx, N, C, L, g_P, g_h, gp_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

@@ -113,7 +113,7 @@ __global__ void gata_fwd_kernel(const float* __restrict__ h, const float* __rest
                                 const float* __restrict__ Ze, int ldz, const float* __restrict__ Y,
                                 const float* __restrict__ fc, const float* __restrict__ kappa,
                                 const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C, int H,
-                                int max_deg, float* __restrict__ h_out, float* __restrict__ Xd_out,
+                                int max_deg, float* __restrict__ h_out, float* __restrict__ Xd_out, float* __restrict__ xd_amax,
                                 float* __restrict__ alpha_out) {
   using Cf = GataCfg<LMAX, SD, ST>;
   constexpr int L = Cf::L, S = Cf::S;
@@ -237,15 +237,17 @@ __global__ void gata_fwd_kernel(const float* __restrict__ h, const float* __rest
     for (int q = 0; q < V; ++q) hv[q] += acc_h[q];
     stv<V>(h_out + (size_t)i * C + c, hv);
   }
+  float xamx = 0.f;
 #pragma unroll
   for (int m = 0; m < L; ++m) {
     const size_t o_ = ((size_t)m * N + i) * C + c;
     float xv[V];
     ldv<V>(Xd + o_, xv);
 #pragma unroll
-    for (int q = 0; q < V; ++q) xv[q] += accX[m][q];
+    for (int q = 0; q < V; ++q) { xv[q] += accX[m][q]; xamx = fmaxf(xamx, fabsf(xv[q])); }
     stv<V>(Xd_out + o_, xv);
   }
+  amax_commit(xd_amax, xamx);
 }
 
 // --------------------------------------------------------- backward, target ---
@@ -573,7 +575,8 @@ static int gata_check(int C, int H, int lmax, int V) {
 int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, const float* x, const float* v,
                     const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                     const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax, int flags,
-                    int max_deg_in, float* h_out, float* Xd_out, float* alpha, cudaStream_t st, bool* handled);
+                    int max_deg_in, float* h_out, float* Xd_out, float* alpha, float* xd_amax, cudaStream_t st,
+                    bool* handled);
 
 int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
@@ -639,7 +642,7 @@ extern "C" {
 int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, const float* x, const float* v,
                    const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                    const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax, int flags,
-                   int max_deg_in, float* h_out, float* Xd_out, float* alpha, void* stream) {
+                   int max_deg_in, float* h_out, float* Xd_out, float* alpha, float* xd_amax, void* stream) {
   const int V = gata_vec(C, H, ldqk, ldz);
   if (gata_check(C, H, lmax, V)) return 1;
   if (N == 0) return 0;
@@ -647,7 +650,7 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
   if (use_staged()) {
     bool handled = false;
     if (gata_fwd_staged(h, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, tgt_ptr, src, N, C, H, lmax, flags, max_deg_in,
-                        h_out, Xd_out, alpha, st, &handled))
+                        h_out, Xd_out, alpha, xd_amax, st, &handled))
       return 1;
     if (handled) return 0;
   }
@@ -656,7 +659,7 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
   const size_t smem = gata_smem_floats(max_deg_in, nparts, H, L, false) * sizeof(float);
   GOTEN_REQUIRE(smem <= 200 * 1024, "max in-degree %d needs %zu B of shared memory", max_deg_in, smem);
   GATA_DISPATCH(gata_fwd_kernel, N, smem, h, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, tgt_ptr, src, N, C, H,
-                max_deg_in, h_out, Xd_out, alpha);
+                max_deg_in, h_out, Xd_out, xd_amax, alpha);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

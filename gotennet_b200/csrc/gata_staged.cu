@@ -111,7 +111,8 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
                                     const float* __restrict__ Y, const float* __restrict__ fc,
                                     const float* __restrict__ kappa, const float* __restrict__ alpha,
                                     const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
-                                    int H, int R, float* __restrict__ h_out, float* __restrict__ Xd_out) {
+                                    int H, int R, float* __restrict__ h_out, float* __restrict__ Xd_out,
+                                    float* __restrict__ xd_amax) {
   using Cf = Cfg<LMAX, SD, ST>;
   constexpr int L = Cf::L, S = Cf::S, ND = Cf::ND;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -206,11 +207,15 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
   }
   if (!act) return;
   st4(h_out + (size_t)i * C + c, add4(ld4(h + (size_t)i * C + c), acc_h));
+  float xamx = 0.f;
 #pragma unroll
   for (int m = 0; m < L; ++m) {
     const size_t o_ = ((size_t)m * N + i) * C + c;
-    st4(Xd_out + o_, add4(ld4(Xd + o_), accX[m]));
+    const float4 xo = add4(ld4(Xd + o_), accX[m]);
+    xamx = amax4(xamx, xo.x, xo.y, xo.z, xo.w);
+    st4(Xd_out + o_, xo);
   }
+  amax_commit(xd_amax, xamx);
 }
 
 // --------------------------------------------------------- backward, target ---
@@ -620,7 +625,8 @@ static inline int multiplier_of_(int lmax, int flags) {
 int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, const float* x, const float* v,
                     const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                     const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax, int flags,
-                    int max_deg_in, float* h_out, float* Xd_out, float* alpha, cudaStream_t st, bool* handled) {
+                    int max_deg_in, float* h_out, float* Xd_out, float* alpha, float* xd_amax, cudaStream_t st,
+                    bool* handled) {
   *handled = false;
   const int D = C / H;
   if (C % 4 != 0 || D % 4 != 0 || ldqk % 4 != 0 || ldz % 4 != 0) return 0;
@@ -652,7 +658,7 @@ int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, 
     GOTEN_CHECK_LAUNCH();
   }
   STAGED_DISPATCH(gata_msg_fwd_kernel, N, block, smem_m, h, Xd, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H,
-                  R, h_out, Xd_out);
+                  R, h_out, Xd_out, xd_amax);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
   return 0;

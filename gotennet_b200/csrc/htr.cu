@@ -187,10 +187,11 @@ template <int LMAX, int V>
 __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                const float* __restrict__ Ze, int ldz, int zt_col0, const float* __restrict__ t,
                                const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
-                               int flags, float* __restrict__ t_out) {
+                               int flags, float* __restrict__ t_out, float* __restrict__ t_amax) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   const int i = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
+  float amx = 0.f;
   float q[L][V];
 #pragma unroll
   for (int m = 0; m < L; ++m) ldv<V>(EQ + ((size_t)m * N + i) * ldp + c, q[m]);
@@ -209,9 +210,11 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(k, qq, kc);
       tv[qq] = fmaf(siluf_(zt[qq]), htr_weight<LMAX>(qc, kc, y, nn, flags), tv[qq]);
+      amx = fmaxf(amx, fabsf(tv[qq]));
     }
     stv<V>(t_out + (size_t)e * C + c, tv);
   }
+  amax_commit(t_amax, amx);
 }
 
 // GY: also produce the geometry gradient g_Y (forces); kept out of the common instantiation (registers)
@@ -222,7 +225,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
                                                  const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src,
                                                  int N, int C, int flags, float* __restrict__ g_EQ,
                                                  float* __restrict__ gZe, int ldgz, float* __restrict__ g_Y,
-                                                 float* __restrict__ gze_amax) {
+                                                 float* __restrict__ gze_amax, float* __restrict__ geq_amax) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   __shared__ EdgeMeta<L> sm;
   __shared__ float red[33];
@@ -296,6 +299,14 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
     for (int m = 0; m < L; ++m) stv<V>(g_EQ + ((size_t)m * N + i) * ldp + c, gq[m]);
   }
   amax_commit(gze_amax, amx);
+  if (geq_amax != nullptr) {
+    float a2 = 0.f;
+#pragma unroll
+    for (int m = 0; m < L; ++m)
+#pragma unroll
+      for (int qq = 0; qq < V; ++qq) a2 = fmaxf(a2, fabsf(gq[m][qq]));
+    amax_commit(geq_amax, a2);
+  }
 }
 
 template <int LMAX, int V>
@@ -304,9 +315,10 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
                                    const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
                                    int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
-                                   float* __restrict__ g_Y, float* __restrict__ gze_amax) {
+                                   float* __restrict__ g_Y, float* __restrict__ gze_amax,
+                                   float* __restrict__ geq_amax) {
   htr_bwd_tgt_body<LMAX, V, false>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
-                                   gze_amax);
+                                   gze_amax, geq_amax);
 }
 template <int LMAX, int V>
 __global__ void htr_bwd_tgt_gy_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
@@ -314,9 +326,10 @@ __global__ void htr_bwd_tgt_gy_kernel(const float* __restrict__ g_t_out, const f
                                       const float* __restrict__ Ze, int ldz, int zt_col0,
                                       const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N,
                                       int C, int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
-                                      float* __restrict__ g_Y, float* __restrict__ gze_amax) {
+                                      float* __restrict__ g_Y, float* __restrict__ gze_amax,
+                                      float* __restrict__ geq_amax) {
   htr_bwd_tgt_body<LMAX, V, true>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
-                                  gze_amax);
+                                  gze_amax, geq_amax);
 }
 
 template <int LMAX, int V>
@@ -325,7 +338,7 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
                                    const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src_perm,
                                    const int32_t* __restrict__ tgt, int N, int C, int flags,
-                                   float* __restrict__ g_EK) {
+                                   float* __restrict__ g_EK, float* __restrict__ gek_amax) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   const int j = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
@@ -356,6 +369,14 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
   }
 #pragma unroll
   for (int m = 0; m < L; ++m) stv<V>(g_EK + ((size_t)m * N + j) * ldp + c, gk[m]);
+  if (gek_amax != nullptr) {
+    float a2 = 0.f;
+#pragma unroll
+    for (int m = 0; m < L; ++m)
+#pragma unroll
+      for (int qq = 0; qq < V; ++qq) a2 = fmaxf(a2, fabsf(gk[m][qq]));
+    amax_commit(gek_amax, a2);
+  }
 }
 
 static inline int block_for(int C, int V) { return (((C + V - 1) / V + 31) / 32) * 32; }
@@ -403,24 +424,24 @@ extern "C" {
 
 int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz, int zt_col0,
                   const float* t, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
-                  float* t_out, void* stream) {
-  HTR_DISPATCH(htr_fwd_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 4, EQ, EK, ldp, Y, Ze, ldz, zt_col0, t, tgt_ptr, src, N, C, flags, t_out);
+                  float* t_out, float* t_amax, void* stream) {
+  HTR_DISPATCH(htr_fwd_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 4, EQ, EK, ldp, Y, Ze, ldz, zt_col0, t, tgt_ptr, src, N, C, flags, t_out, t_amax);
 }
 
 int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
-                      float* g_EQ, float* gZe, int ldgz, float* g_Y, float* gze_amax, void* stream) {
+                      float* g_EQ, float* gZe, int ldgz, float* g_Y, float* gze_amax, float* geq_amax, void* stream) {
   if (g_Y != nullptr)
     HTR_DISPATCH(htr_bwd_tgt_gy_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
-                 g_Y, gze_amax);
+                 g_Y, gze_amax, geq_amax);
   HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
-               g_Y, gze_amax);
+               g_Y, gze_amax, geq_amax);
 }
 
 int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* src_ptr, const int32_t* src_perm, const int32_t* tgt, int N, int C,
-                      int lmax, int flags, float* g_EK, void* stream) {
-  HTR_DISPATCH(htr_bwd_src_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 2, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, src_ptr, src_perm, tgt, N, C, flags, g_EK);
+                      int lmax, int flags, float* g_EK, float* gek_amax, void* stream) {
+  HTR_DISPATCH(htr_bwd_src_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0), 2, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, src_ptr, src_perm, tgt, N, C, flags, g_EK, gek_amax);
 }
 
 }  // extern "C"

@@ -139,12 +139,16 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ g_y, const float* _
 // ------------------------------------------------------------- EdgeInit ------
 __global__ void edge_init_fwd_kernel(const float* __restrict__ h, const float* __restrict__ F, int ldf, int col0,
                                      const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, int64_t E, int C,
-                                     float* __restrict__ t) {
+                                     float* __restrict__ t, float* __restrict__ t_amax) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= E * C) return;
-  const int64_t e = idx / C;
-  const int c = (int)(idx % C);
-  t[idx] = (h[(int64_t)tgt[e] * C + c] + h[(int64_t)src[e] * C + c]) * F[e * ldf + col0 + c];
+  float v = 0.f;
+  if (idx < E * C) {
+    const int64_t e = idx / C;
+    const int c = (int)(idx % C);
+    v = (h[(int64_t)tgt[e] * C + c] + h[(int64_t)src[e] * C + c]) * F[e * ldf + col0 + c];
+    t[idx] = v;
+  }
+  block_amax_commit(t_amax, fabsf(v));
 }
 
 __global__ void edge_init_bwd_edge_kernel(const float* __restrict__ g_t, const float* __restrict__ h,
@@ -232,10 +236,10 @@ int goten_ln_silu_bwd(const float* g_y, const float* x, const float* gamma, cons
 }
 
 int goten_edge_init_fwd(const float* h, const float* F, int ldf, int col0, const int32_t* src, const int32_t* tgt,
-                        int64_t E, int C, float* t, void* stream) {
+                        int64_t E, int C, float* t, float* t_amax, void* stream) {
   if (E * C == 0) return 0;
   edge_init_fwd_kernel<<<(unsigned)cdiv64(E * C, 256), 256, 0, as_stream(stream)>>>(h, F, ldf, col0, src, tgt, E, C,
-                                                                                   t);
+                                                                                   t, t_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

@@ -142,8 +142,9 @@ class GATA(nn.Module):
                 "htr_flags": (1 if self.sep_htr else 0) | (2 if self.update_info["rej"] else 0),
                 "vk_groups": groups}
 
-    def _block(self, plan: GraphPlan, h, Xd, t, Y, fc, kappa):
-        """h [N,C], Xd [L,N,C], t [E,C] in plan order -> (h', Xd', t')."""
+    def _block(self, plan: GraphPlan, h, Xd, t, Y, fc, kappa, t_amax=None):
+        """h [N,C], Xd [L,N,C], t [E,C] in plan order -> (h', Xd', t', hints); hints = [max|Xd'|, max|t'|] device
+        scalars written by the kernels (operand scales of the next GEMMs), t_amax = the same for the input t."""
         if self.dropout > 0 and self.training:
             raise NotImplementedError("attention dropout in training mode is not implemented (use attn_dropout=0)")
         Wn1 = torch.cat([self.W_q.weight, self.W_k.weight, self.gamma_s[0].weight, self.gamma_v[0].weight], 0)
@@ -161,10 +162,10 @@ class GATA(nn.Module):
             Wvq = Wvk = None
         out = ops.GataBlockFn.apply(h, Xd, t, Y, fc, kappa, Wn1, bn1, self.gamma_s[1].weight, self.gamma_s[1].bias,
                                     self.gamma_v[1].weight, self.gamma_v[1].bias, We, be, Wvq, Wvk, plan,
-                                    self._kernel_cfg())
+                                    self._kernel_cfg(), t_amax)
         if self.has_htr:
             return out
-        return out[0], out[1], t
+        return out[0], out[1], t, out[2]
 
     def forward(self, edge_index: Tensor, h: Tensor, X: Tensor, rl_ij: Tensor, t_ij: Tensor, r_ij: Tensor,
                 n_edges: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
@@ -178,7 +179,7 @@ class GATA(nn.Module):
         fc = self.cutoff(r).contiguous()
         kappa = (torch.sqrt(ne.float()) if self.scale_edge else torch.ones_like(r)) / (C ** 0.5)
         Xd = ops.PermuteFn.apply(X, True)
-        h1, Xd1, t1 = self._block(plan, h.reshape(N, C).contiguous(), Xd, t.contiguous(), rl.contiguous().float(), fc,
+        h1, Xd1, t1, _ = self._block(plan, h.reshape(N, C).contiguous(), Xd, t.contiguous(), rl.contiguous().float(), fc,
                                   kappa.contiguous())
         if plan.order is not None:
             inv = torch.empty_like(plan.order)
@@ -206,9 +207,9 @@ class EQFF(nn.Module):
         for l in self.gamma_m:
             l.reset_parameters()
 
-    def _block(self, h, Xd):
+    def _block(self, h, Xd, xd_amax=None):
         return ops.EqffBlockFn.apply(h, Xd, self.W_vu.weight, self.gamma_m[0].weight, self.gamma_m[0].bias,
-                                     self.gamma_m[1].weight, self.gamma_m[1].bias, self.epsilon)
+                                     self.gamma_m[1].weight, self.gamma_m[1].bias, self.epsilon, xd_amax)
 
     def forward(self, h: Tensor, X: Tensor) -> Tuple[Tensor, Tensor]:
         """h [N,1,C], X [N,L,C] -> same shapes."""
@@ -313,15 +314,17 @@ class GotenNet(nn.Module):
         ndp, d0, d1 = ni.W_ndp.dense_layers[0], ni.W_nrd_nru.dense_layers[0], ni.W_nrd_nru.dense_layers[1]
         Wphi = torch.cat([ndp.weight, ei.W_erp.weight], 0)
         bphi = torch.cat([ndp.bias, ei.W_erp.bias], 0)
-        h, t = ops.InitBlockFn.apply(h0, hnbr, phi, fc, Wphi, bphi, d0.weight, d0.bias, d0.norm.weight, d0.norm.bias,
-                                     d1.weight, d1.bias, plan, d0.norm.eps)
+        h, t, t_amax = ops.InitBlockFn.apply(h0, hnbr, phi, fc, Wphi, bphi, d0.weight, d0.bias, d0.norm.weight,
+                                             d0.norm.bias, d1.weight, d1.bias, plan, d0.norm.eps)
         Xd = torch.zeros(L, plan.N, C, device=h.device, dtype=torch.float32)  # always fp32 (gotennet.py:992)
         cap = getattr(self, "_capture", None)  # test hook: per-layer states
         if cap is not None:
             cap.update(h0=h.detach(), t0=t.detach(), Y=Y.detach(), phi=phi.detach(), fc=fc.detach())
         for i, (gata, eqff) in enumerate(zip(self.gata_list, self.eqff_list)):
-            h, Xd, t = gata._block(plan, h, Xd, t, Y, fc, kappa)
-            h, Xd = eqff._block(h, Xd)
+            has_htr = gata.has_htr
+            h, Xd, t, hints = gata._block(plan, h, Xd, t, Y, fc, kappa, t_amax)
+            t_amax = hints[1:2] if has_htr else t_amax
+            h, Xd = eqff._block(h, Xd, hints[0:1])
             if cap is not None:
                 cap[f"h{i + 1}"], cap[f"t{i + 1}"] = h.detach(), t.detach()
                 cap[f"X{i + 1}"] = Xd.detach().permute(1, 0, 2)

@@ -298,14 +298,17 @@ class InitBlockFn(torch.autograd.Function):
                 _ptr(rstd), st)
         h = linear_fwd(y2, W2, b2)
         t = torch.empty(E, C, device=dev)
-        L_.call("goten_edge_init_fwd", _ptr(h), _ptr(F), 2 * C, C, _ptr(plan.src), _ptr(plan.tgt), E, C, _ptr(t), st)
+        t_amax = torch.zeros(1, device=dev)  # max |t|, written by the kernel (operand scale of the first edge GEMM)
+        L_.call("goten_edge_init_fwd", _ptr(h), _ptr(F), 2 * C, C, _ptr(plan.src), _ptr(plan.tgt), E, C, _ptr(t),
+                _ptr(t_amax), st)
         ctx.plan = plan
         ctx.save_for_backward(hnbr, phi, fc, Wphi, W1, ln_g, ln_b, W2, F, ctx0, y1, y2, mean, rstd, h)
-        return h, t
+        ctx.mark_non_differentiable(t_amax)
+        return h, t, t_amax
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g_h, g_t):
+    def backward(ctx, g_h, g_t, _g_amax=None):
         hnbr, phi, fc, Wphi, W1, ln_g, ln_b, W2, F, ctx0, y1, y2, mean, rstd, h = ctx.saved_tensors
         plan = ctx.plan
         L_ = lib()
@@ -363,7 +366,7 @@ class GataBlockFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, plan, cfg):
+    def forward(ctx, h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, plan, cfg, t_amax=None):
         _chk(h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk)
         L_ = lib()
         st = _stream()
@@ -376,6 +379,7 @@ class GataBlockFn(torch.autograd.Function):
         dev = h.device
         SC = S * C
         am = AmaxScope()
+        am.put(t, t_amax)  # max |t| from the kernel that produced t (None: measured on first use)
         # node projections: Z1 = [q | k | pre_s | pre_v], A1 = silu(Z1[:, 2C:])
         Z1 = torch.empty(N, 4 * C, device=dev)
         A1 = torch.empty(N, 2 * C, device=dev)
@@ -392,9 +396,12 @@ class GataBlockFn(torch.autograd.Function):
         h1 = torch.empty_like(h)
         Xd1 = torch.empty_like(Xd)
         alpha = torch.empty(E, H, device=dev)
+        hints = torch.zeros(2, device=dev)  # [max |Xd1|, max |t1|], written by the producing kernels
+        xd_amax, t1_amax = hints[0:1], hints[1:2]
+        am.put(Xd1, xd_amax)
         L_.call("goten_gata_fwd", _ptr(h), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze), ldz, _ptr(Y),
                 _ptr(fc), _ptr(kappa), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax, cfg["gata_flags"],
-                plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), st)
+                plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), _ptr(xd_amax), st)
         EQK = Wqk = None
         t1 = t
         if htr:
@@ -409,19 +416,22 @@ class GataBlockFn(torch.autograd.Function):
                      c_off=lo * N * 2 * C, am=am)
             t1 = torch.empty_like(t)
             L_.call("goten_htr_fwd", _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, (S + 1) * C, _ptr(t),
-                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(t1), st)
+                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(t1), _ptr(t1_amax), st)
         ctx.plan, ctx.cfg, ctx.htr = plan, cfg, htr
         amx = am.export([h, t, Wn1, Ws2, Wv2, We, Wqk, A1, Xd1 if htr else None])
         ctx.n_amax = len(amx)
         ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wqk, Z1, A1, x, v, Ze, alpha, Xd1, EQK, *amx)
+        ctx.mark_non_differentiable(hints)
         if htr:
-            return h1, Xd1, t1
-        return h1, Xd1  # last layer: t_ij passes through unchanged (gotennet.py:449-450)
+            return h1, Xd1, t1, hints
+        return h1, Xd1, hints  # last layer: t_ij passes through unchanged (gotennet.py:449-450)
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, g_h1, g_Xd1, g_t1=None):
+    def backward(ctx, g_h1, g_Xd1, g_t1=None, _g_hints=None):
         saved = ctx.saved_tensors
+        if not ctx.htr:
+            g_t1 = None  # (third output of the last layer is the hint tensor)
         (h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wqk, Z1, A1, x, v, Ze, alpha, Xd1, EQK) = saved[:19]
         plan, cfg, htr = ctx.plan, ctx.cfg, ctx.htr
         am = AmaxScope()
@@ -451,13 +461,15 @@ class GataBlockFn(torch.autograd.Function):
             if g_t1 is None:
                 g_t1 = torch.zeros(E, C, device=dev)
             g_EQK = torch.empty_like(EQK)  # rows [g_EQ | g_EK], pitch 2C
+            geqk_amax = am.slot(dev) if am.enabled else None
+            am.put(g_EQK, geqk_amax)
             zt0 = (S + 1) * C
             L_.call("goten_htr_bwd_tgt", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, zt0,
                     _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(g_EQK), _ptr(gZe), ldz,
-                    _ptr(g_Y), _ptr(gze_amax), st)
+                    _ptr(g_Y), _ptr(gze_amax), _ptr(geqk_amax), st)
             L_.call("goten_htr_bwd_src", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, zt0,
                     _ptr(plan.src_ptr), _ptr(plan.src_perm), _ptr(plan.tgt), N, C, lmax, cfg["htr_flags"],
-                    _ptr(g_EQK, C), st)
+                    _ptr(g_EQK, C), _ptr(geqk_amax), st)
             # X gradient: g_Xm^l = g_Xd1^l + [g_EQ | g_EK]^l [W_vq; W_vk,l] (one K = 2C GEMM per degree group, the
             # residual added once); weight gradients of the stacked weight, un-stacked below
             G = len(cfg["vk_groups"])
@@ -512,7 +524,8 @@ class GataBlockFn(torch.autograd.Function):
         else:
             dWe.zero_()
             dbe.zero_()
-        return (g_h, g_Xd, g_t, g_Y, g_fc, None, dWn1, dbn1, dWs2, dbs2, dWv2, dbv2, dWe, dbe, dWvq, dWvk, None, None)
+        return (g_h, g_Xd, g_t, g_Y, g_fc, None, dWn1, dbn1, dWs2, dbs2, dWv2, dbv2, dWe, dbe, dWvq, dWvk, None, None,
+                None)
 
 
 # ---------------------------------------------------------------------------
@@ -520,7 +533,7 @@ class GataBlockFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 class EqffBlockFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, h, Xd, Wvu, Wm1, bm1, Wm2, bm2, eps):
+    def forward(ctx, h, Xd, Wvu, Wm1, bm1, Wm2, bm2, eps, xd_amax=None):
         _chk(h, Xd, Wvu, Wm1, bm1, Wm2, bm2)
         L_ = lib()
         st = _stream()
@@ -528,6 +541,7 @@ class EqffBlockFn(torch.autograd.Function):
         L = Xd.shape[0]
         dev = h.device
         am = AmaxScope()
+        am.put(Xd, xd_amax)  # max |Xd| from the GATA kernel that produced it (None: measured on first use)
         P = torch.empty_like(Xd)
         gemm(Xd, C, 0, Wvu, C, 1, P, C, L * N, C, C, am=am)
         cx = torch.empty(N, 2 * C, device=dev)
@@ -563,13 +577,15 @@ class EqffBlockFn(torch.autograd.Function):
         g_cx, dWm1, dbm1 = linear_bwd(g_Zm, cx, Wm1, am=am)
         g_P = torch.empty_like(P)
         g_h = torch.empty(N, C, device=dev)
+        gp_amax = am.slot(dev) if am.enabled else None
+        am.put(g_P, gp_amax)
         L_.call("goten_eqff_ctx_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(g_cx), _ptr(P), _ptr(M), _ptr(cx), N, C, L,
-                _ptr(g_P), _ptr(g_h), st)
+                _ptr(g_P), _ptr(g_h), _ptr(gp_amax), st)
         g_Xd = torch.empty_like(Xd)
         gemm(g_P, C, 0, Wvu, C, 0, g_Xd, C, L * N, C, C, add_src=g_Xd2, ld_add=C, am=am)
         dWvu = torch.empty_like(Wvu)
         gemm(g_P, C, 1, Xd, C, 0, dWvu, C, C, C, L * N, am=am)
-        return g_h, g_Xd, dWvu, dWm1, dbm1, dWm2, dbm2, None
+        return g_h, g_Xd, dWvu, dWm1, dbm1, dWm2, dbm2, None, None
 
 
 # ---------------------------------------------------------------------------

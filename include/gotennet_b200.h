@@ -128,7 +128,11 @@ int goten_gemm_scaled(const float* A, int lda, int trans_a, const float* B, int 
                       const float* add_src, int ld_add, float* act_out, int ld_act, int act_lo,
                       int act_hi, float* colsum, const float* a_amax, const float* b_amax,
                       void* workspace, int64_t workspace_bytes, int impl, void* stream);
-/* out[0] = max(out[0], max |A[m][n]|) over a [M][N] matrix (ld = lda); out must hold a
+/* Kernels that produce a large GEMM operand take an optional trailing `*_amax` DEVICE
+ * pointer (t_amax, xd_amax, gze_amax, geq_amax, gek_amax, gp_amax): a running
+ * max |value written| (atomic max on a non-negative float the caller zeroed), so the
+ * operand needs no separate goten_absmax pass.  NULL disables it.
+ * out[0] = max(out[0], max |A[m][n]|) over a [M][N] matrix (ld = lda); out must hold a
  * non-negative float (zero it first for a plain maximum).                                */
 int goten_absmax(const float* A, int64_t lda, int64_t M, int N, float* out, void* stream);
 /* out[m][n] = g[m][n] * silu'(pre[m][n])  (Dense activation backward, layers.py:527-528) */
@@ -162,7 +166,8 @@ int goten_ln_silu_bwd(const float* g_y, const float* x, const float* gamma, cons
                       float* g_gamma_part, float* g_beta_part, int n_part, void* stream);
 /* EdgeInit.message (layers.py:1711): t[e][c] = (h[i][c] + h[j][c]) * F[e][C + c]  (self loops kept) */
 int goten_edge_init_fwd(const float* h, const float* F, int ldf, int col0, const int32_t* src,
-                        const int32_t* tgt, int64_t n_edges, int C, float* t, void* stream);
+                        const int32_t* tgt, int64_t n_edges, int C, float* t, float* t_amax,
+                        void* stream);
 /* gF[e][col0+c] = g_t[e][c]*(h_i+h_j);  g_h[n][c] = sum_{e: tgt=n} g_t*F + sum_{e: src=n} g_t*F */
 int goten_edge_init_bwd(const float* g_t, const float* h, const float* F, int ldf, int col0,
                         const int32_t* tgt_ptr, const int32_t* src, const int32_t* tgt,
@@ -182,7 +187,7 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
                    const float* v, const float* Ze, int ldz, const float* Y, const float* fc,
                    const float* kappa, const int32_t* tgt_ptr, const int32_t* src, int n_nodes,
                    int C, int H, int lmax, int flags, int max_deg_in, float* h_out, float* Xd_out,
-                   float* alpha, void* stream);
+                   float* alpha, float* xd_amax, void* stream);
 /* backward, target-centric half: needs g_h[N][C], g_Xd[L][N][C] (gradients of the
  * block outputs).  Produces g_qk[:, 0:C) (dq), gZe[:, 0:(S+1)C) (d pre-act W_re, d filter),
  * da[E][H] (gradient of the attention logits) and, if non-NULL, the geometry
@@ -214,17 +219,19 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
  * bit1 = rejection enabled.                                                    */
 int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                   int zt_col0, const float* t, const int32_t* tgt_ptr, const int32_t* src,
-                  int n_nodes, int C, int lmax, int flags, float* t_out, void* stream);
+                  int n_nodes, int C, int lmax, int flags, float* t_out, float* t_amax,
+                  void* stream);
 /* target half: g_EQ[L][N][C], gZe[:, zt_col0..) = g_t_out * w * silu'(zt); optional g_Y (accumulated) */
 int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y,
                       const float* Ze, int ldz, int zt_col0, const int32_t* tgt_ptr,
                       const int32_t* src, int n_nodes, int C, int lmax, int flags, float* g_EQ,
-                      float* gZe, int ldgz, float* g_Y, float* gze_amax, void* stream);
+                      float* gZe, int ldgz, float* g_Y, float* gze_amax, float* geq_amax,
+                      void* stream);
 /* source half: g_EK[L][N][C] */
 int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y,
                       const float* Ze, int ldz, int zt_col0, const int32_t* src_ptr,
                       const int32_t* src_perm, const int32_t* tgt, int n_nodes, int C, int lmax,
-                      int flags, float* g_EK, void* stream);
+                      int flags, float* g_EK, float* gek_amax, void* stream);
 
 /* ------------------------------------------------------------ EQFF block --
  * EQFF.forward (gotennet.py:728-748). P = X W_vu^T comes from goten_gemm.
@@ -240,7 +247,7 @@ int goten_eqff_update_bwd(const float* g_h_out, const float* g_Xd_out, const flo
 /* g_P = g_Xd_out * m2 + g_ctx[:, C:] * P / n ;  g_h = g_h_out + g_ctx[:, :C]  (n = ctx[:, C:]) */
 int goten_eqff_ctx_bwd(const float* g_h_out, const float* g_Xd_out, const float* g_ctx,
                        const float* P, const float* m, const float* ctx, int n_nodes, int C, int L,
-                       float* g_P, float* g_h, void* stream);
+                       float* g_P, float* g_h, float* gp_amax, void* stream);
 
 /* ------------------------------------------------------------ utilities --
  * out = a + b (gradient joins), layout change [N][L][C] <-> [L][N][C], row gather
