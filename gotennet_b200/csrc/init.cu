@@ -137,28 +137,49 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ g_y, const float* _
 }
 
 // ------------------------------------------------------------- EdgeInit ------
+// V = 4: one 128-bit access per array and thread (C, ldf, col0 multiples of 4 and 16 B aligned bases); V = 1 fallback
+template <int V>
 __global__ void edge_init_fwd_kernel(const float* __restrict__ h, const float* __restrict__ F, int ldf, int col0,
                                      const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, int64_t E, int C,
                                      float* __restrict__ t, float* __restrict__ t_amax) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float v = 0.f;
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+  float amx = 0.f;
   if (idx < E * C) {
     const int64_t e = idx / C;
-    const int c = (int)(idx % C);
-    v = (h[(int64_t)tgt[e] * C + c] + h[(int64_t)src[e] * C + c]) * F[e * ldf + col0 + c];
-    t[idx] = v;
+    const int c = (int)(idx - e * C);
+    if (V == 4) {
+      const float4 hi = *reinterpret_cast<const float4*>(h + (int64_t)tgt[e] * C + c);
+      const float4 hj = *reinterpret_cast<const float4*>(h + (int64_t)src[e] * C + c);
+      const float4 f = *reinterpret_cast<const float4*>(F + e * ldf + col0 + c);
+      const float4 v = make_float4((hi.x + hj.x) * f.x, (hi.y + hj.y) * f.y, (hi.z + hj.z) * f.z, (hi.w + hj.w) * f.w);
+      *reinterpret_cast<float4*>(t + idx) = v;
+      amx = amax4(0.f, v.x, v.y, v.z, v.w);
+    } else {
+      const float v = (h[(int64_t)tgt[e] * C + c] + h[(int64_t)src[e] * C + c]) * F[e * ldf + col0 + c];
+      t[idx] = v;
+      amx = fabsf(v);
+    }
   }
-  block_amax_commit(t_amax, fabsf(v));
+  block_amax_commit(t_amax, amx);
 }
 
+template <int V>
 __global__ void edge_init_bwd_edge_kernel(const float* __restrict__ g_t, const float* __restrict__ h,
                                           const int32_t* __restrict__ src, const int32_t* __restrict__ tgt, int64_t E,
                                           int C, float* __restrict__ gF, int ldgf, int col0) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
   if (idx >= E * C) return;
   const int64_t e = idx / C;
-  const int c = (int)(idx % C);
-  gF[e * ldgf + col0 + c] = g_t[idx] * (h[(int64_t)tgt[e] * C + c] + h[(int64_t)src[e] * C + c]);
+  const int c = (int)(idx - e * C);
+  if (V == 4) {
+    const float4 hi = *reinterpret_cast<const float4*>(h + (int64_t)tgt[e] * C + c);
+    const float4 hj = *reinterpret_cast<const float4*>(h + (int64_t)src[e] * C + c);
+    const float4 g = *reinterpret_cast<const float4*>(g_t + idx);
+    *reinterpret_cast<float4*>(gF + e * ldgf + col0 + c) =
+        make_float4(g.x * (hi.x + hj.x), g.y * (hi.y + hj.y), g.z * (hi.z + hj.z), g.w * (hi.w + hj.w));
+  } else {
+    gF[e * ldgf + col0 + c] = g_t[idx] * (h[(int64_t)tgt[e] * C + c] + h[(int64_t)src[e] * C + c]);
+  }
 }
 
 __global__ void edge_init_bwd_node_kernel(const float* __restrict__ g_t, const float* __restrict__ F, int ldf, int col0,
@@ -178,6 +199,8 @@ __global__ void edge_init_bwd_node_kernel(const float* __restrict__ g_t, const f
   }
   g_h[idx] = acc;
 }
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace goten
 
@@ -238,8 +261,12 @@ int goten_ln_silu_bwd(const float* g_y, const float* x, const float* gamma, cons
 int goten_edge_init_fwd(const float* h, const float* F, int ldf, int col0, const int32_t* src, const int32_t* tgt,
                         int64_t E, int C, float* t, float* t_amax, void* stream) {
   if (E * C == 0) return 0;
-  edge_init_fwd_kernel<<<(unsigned)cdiv64(E * C, 256), 256, 0, as_stream(stream)>>>(h, F, ldf, col0, src, tgt, E, C,
-                                                                                   t, t_amax);
+  if (C % 4 == 0 && ldf % 4 == 0 && col0 % 4 == 0 && al16(h) && al16(F) && al16(t))
+    edge_init_fwd_kernel<4><<<(unsigned)cdiv64(E * C / 4, 256), 256, 0, as_stream(stream)>>>(h, F, ldf, col0, src, tgt,
+                                                                                            E, C, t, t_amax);
+  else
+    edge_init_fwd_kernel<1><<<(unsigned)cdiv64(E * C, 256), 256, 0, as_stream(stream)>>>(h, F, ldf, col0, src, tgt, E,
+                                                                                        C, t, t_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }
@@ -250,7 +277,11 @@ int goten_edge_init_bwd(const float* g_t, const float* h, const float* F, int ld
   cudaStream_t st = as_stream(stream);
   if ((int64_t)N * C == 0) return 0;
   if (E * C > 0) {
-    edge_init_bwd_edge_kernel<<<(unsigned)cdiv64(E * C, 256), 256, 0, st>>>(g_t, h, src, tgt, E, C, gF, ldgf, col0);
+    if (C % 4 == 0 && ldgf % 4 == 0 && col0 % 4 == 0 && al16(h) && al16(g_t) && al16(gF))
+      edge_init_bwd_edge_kernel<4><<<(unsigned)cdiv64(E * C / 4, 256), 256, 0, st>>>(g_t, h, src, tgt, E, C, gF, ldgf,
+                                                                                    col0);
+    else
+      edge_init_bwd_edge_kernel<1><<<(unsigned)cdiv64(E * C, 256), 256, 0, st>>>(g_t, h, src, tgt, E, C, gF, ldgf, col0);
     GOTEN_CHECK_LAUNCH();
   }
   edge_init_bwd_node_kernel<<<(unsigned)cdiv64((int64_t)N * C, 256), 256, 0, st>>>(g_t, F, ldf, col0, tgt_ptr,
