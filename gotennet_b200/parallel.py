@@ -44,9 +44,15 @@ class FlatGradBuffer:
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params = [p for p in params if p.requires_grad]
         self.sizes = [p.numel() for p in self.params]
+        # every tensor starts on a 16-byte boundary (vector loads in the kernels); the padding stays zero
+        self.offsets, off = [], 0
+        for n in self.sizes:
+            self.offsets.append(off)
+            off += (n + 3) & ~3
+        self.numel = off
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=dev)
-        self.views = [v.view_as(p) for v, p in zip(self.flat.split(self.sizes), self.params)]
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self.views = [self.flat[o:o + n].view_as(p) for o, n, p in zip(self.offsets, self.sizes, self.params)]
 
     def pack(self) -> torch.Tensor:
         srcs, dsts = [], []

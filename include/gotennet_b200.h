@@ -283,6 +283,22 @@ int goten_atomwise_reduce_bwd(const float* g_y, const float* g_yi, const float* 
 int goten_act_fwd(int kind, const float* x, int64_t n, float* y, void* stream);
 int goten_act_bwd(int kind, const float* g, const float* x, int64_t n, float* out, void* stream);
 
+/* --------------------------------------------------------------- optimiser --
+ * Training step of the reference on one FLAT fp32 parameter buffer
+ * (models/goten_model.py:521-578: torch.optim.AdamW(eps=1e-7), weight decay on every
+ * parameter; configs/trainer/default.yaml:10: gradient_clip_val 5.0, norm clipping).
+ * goten_sumsq: out[0] = sum g[i]^2, deterministic (two stages, no atomics); `partial`
+ *   holds goten_sumsq_workspace_floats() floats.
+ * goten_adamw_step: g' = g * grad_scale * min(1, max_norm / (sqrt(sumsq[0]) * grad_scale + 1e-6))
+ *   (max_norm <= 0 or sumsq NULL: no clipping), then the torch.optim.AdamW update of
+ *   p, m (exp_avg), v (exp_avg_sq) in place.  bias_c1 = 1 - beta1^step, bias_c2 = 1 - beta2^step.
+ *   The clip coefficient is formed on the device: no host read between backward and step. */
+int goten_sumsq(const float* g, int64_t n, float* partial, float* out, void* stream);
+int goten_sumsq_workspace_floats(void);
+int goten_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, float bias_c1, float bias_c2,
+                     float max_norm, const float* sumsq, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

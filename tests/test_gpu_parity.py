@@ -400,3 +400,63 @@ def test_head_modes_and_batch_checks(g, dev):
     d.z, d.batch, d.representation = z.to(dev), batch.flip(0).to(dev), h.to(dev)
     with pytest.raises(g.GotenError):
         head(d)  # unsorted batch vector
+
+
+# ------------------------------------------------------------- optimiser -----
+@pytest.mark.gpu
+@pytest.mark.parametrize("clip", [None, 0.5])
+def test_fused_adamw_matches_torch(g, dev, clip):
+    """FusedAdamW (flat buffers, clip coefficient on the device) vs torch.optim.AdamW + clip_grad_norm_ on the CPU:
+    the optimiser the reference configures (goten_model.py:528-534, eps=1e-7; trainer gradient_clip_val)."""
+    gen = torch.Generator().manual_seed(3)
+    shapes = [(7, 5), (33,), (64, 64), (3,), (130, 17)]   # odd sizes: padded slots and the scalar tails
+    ref_p = [torch.nn.Parameter(torch.randn(*s, generator=gen)) for s in shapes]
+    our_p = [torch.nn.Parameter(p.detach().clone().to(dev)) for p in ref_p]
+    ref = torch.optim.AdamW(ref_p, lr=3e-3, weight_decay=0.05, eps=1e-7)
+    ours = g.FusedAdamW(our_p, lr=3e-3, weight_decay=0.05, eps=1e-7, max_grad_norm=clip)
+    for step in range(6):
+        lr = 3e-3 * min(1.0, (step + 1) / 4)              # warm-up rewrites param_groups[*]["lr"] (goten_model.py:565-570)
+        for pg in ref.param_groups:
+            pg["lr"] = lr
+        for pg in ours.param_groups:
+            pg["lr"] = lr
+        grads = [torch.randn(*s, generator=gen) * (10.0 ** (step % 3 - 1)) for s in shapes]
+        for p, q, gr in zip(ref_p, our_p, grads):
+            p.grad = gr.clone()
+            q.grad = gr.to(dev)
+        total = torch.nn.utils.clip_grad_norm_(ref_p, clip) if clip else torch.sqrt(sum((x ** 2).sum() for x in grads))
+        ref.step()
+        ours.step()
+        assert abs(float(ours.grad_norm) - float(total)) <= 1e-5 * float(total)
+        for p, q in zip(ref_p, our_p):
+            assert rel(q.data, p.data) < 2e-6
+    sd = ours.state_dict()
+    assert sd["step"] == 6 and sd["exp_avg"].numel() == ours.flat_p.numel()
+
+
+@pytest.mark.gpu
+def test_training_steps_with_fused_optimizer(g, dev):
+    """Parameters re-pointed into the flat buffer keep working as kernel operands: a few clipped AdamW steps on the
+    energy of a small batch reduce the loss, and every Parameter still aliases the flat storage afterwards."""
+    from gotennet_b200.synthetic import synth_batch
+    torch.manual_seed(0)
+    model = g.GotenNetWrapper(n_atom_basis=64, n_interactions=2, lmax=2, cutoff_fn=g.CosineCutoff(5.0), sep_dir=True,
+                              sep_tensor=True).to(dev)
+    head = g.Atomwise(n_in=64, activation="swish").to(dev)
+    params = list(model.parameters()) + list(head.parameters())
+    opt = g.FusedAdamW(params, lr=2e-3, weight_decay=0.0, max_grad_norm=5.0)
+    z, pos, batch = synth_batch("qm9", 16, seed=5)
+    target = torch.linspace(-1.0, 1.0, 16, device=dev).unsqueeze(1)
+    losses = []
+    for _ in range(8):
+        d = Data()
+        d.z, d.pos, d.batch, d.num_graphs = z.to(dev), pos.to(dev), batch.to(dev), 16
+        d.representation, d.vector_representation = model(d)
+        loss = (head(d)["y"] - target).pow(2).mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert losses[-1] < 0.7 * losses[0], losses
+    lo, hi = opt.flat_p.data_ptr(), opt.flat_p.data_ptr() + 4 * opt.flat_p.numel()
+    assert all(lo <= p.data_ptr() < hi for p in params)
