@@ -72,6 +72,32 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
   return t;
 }
 
+// Block-wide sums of NV per-thread values with ONE barrier (geometry gradients: per edge, 1 + L channel sums).
+// Every thread stores its values into `scratch` (row pitch blockDim + 4 floats: the quad reads below are bank-conflict
+// free), one __syncthreads, then quads of threads add one row each and quad lane 0 hands the total to sink(v, sum).
+// Fixed summation order: results are run-to-run identical.  Callers alternate between two scratch buffers on
+// consecutive calls (a buffer is re-written only after the next call's barrier, i.e. after everybody has read it) and
+// must call with all threads of the block.  Floats needed per buffer: NV * (blockDim + 4).
+template <int NV, class Sink>
+__device__ __forceinline__ void block_sums_one_barrier(const float (&vals)[NV], float* scratch, Sink sink) {
+  const int pitch = blockDim.x + 4;
+#pragma unroll
+  for (int v = 0; v < NV; ++v) scratch[v * pitch + threadIdx.x] = vals[v];
+  __syncthreads();
+  const int r = threadIdx.x & 3;
+  for (int v0 = 0; v0 < NV; v0 += (int)(blockDim.x >> 2)) {   // uniform trip count: the shuffles see all lanes
+    const int v = v0 + (int)(threadIdx.x >> 2);
+    float s = 0.f;
+    if (v < NV) {
+      const float* row = scratch + v * pitch;
+      for (int i = r; i < (int)blockDim.x; i += 4) s += row[i];
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (v < NV && r == 0) sink(v, s);
+  }
+}
+
 // Running max |.| of the values a kernel writes into a GEMM operand: the split-fp16 GEMM (gemm_tc16.cu) scales its
 // operands by a power of two derived from this bound.  `out` holds a non-negative float, compared as unsigned bits.
 __device__ __forceinline__ float amax4(float m, float a, float b, float c, float d) {

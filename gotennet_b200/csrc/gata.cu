@@ -93,6 +93,9 @@ __host__ __device__ inline size_t gata_smem_floats(int max_deg, int nparts, int 
   if (bwd) n += (size_t)max_deg * H;
   return n;
 }
+// extra floats of the target backward when geometry gradients are requested: two scratch buffers of
+// (1 + L) x (block + 4) for block_sums_one_barrier
+__host__ __device__ inline size_t gata_geo_floats(int block, int L) { return (size_t)2 * (1 + L) * (block + 4); }
 
 __device__ __forceinline__ GataSmem carve(float* base, int max_deg, int nparts, int H, int L, bool bwd) {
   GataSmem s;
@@ -268,7 +271,6 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
   float amx = 0.f;
   constexpr int L = Cf::L, S = Cf::S;
   extern __shared__ float smem_f[];
-  __shared__ float red[33];
   const int i = blockIdx.x, c = threadIdx.x * V;
   const bool act = c < C;
   const int D = C / H;
@@ -417,16 +419,16 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
         }
       }
     }
-    if (g_fc != nullptr) {  // block-uniform branches
-      const float s = block_sum(gfc_part, red);
-      if (threadIdx.x == 0) g_fc[e] += s;
-    }
-    if (g_Y != nullptr) {
+    if (geom) {  // block-uniform: the 1 + L channel sums of this edge with one barrier
+      float vals[1 + L];
+      vals[0] = gfc_part;
 #pragma unroll
-      for (int m = 0; m < L; ++m) {
-        const float s = block_sum(gy_part[m], red);
-        if (threadIdx.x == 0) g_Y[e * L + m] += s;
-      }
+      for (int m = 0; m < L; ++m) vals[1 + m] = gy_part[m];
+      float* scratch = smem_f + gata_smem_floats(max_deg, nparts, H, L, true) + (size_t)(t & 1) * (1 + L) * (blockDim.x + 4);
+      block_sums_one_barrier<1 + L>(vals, scratch, [&](int v, float s) {
+        if (v == 0) { if (g_fc != nullptr) g_fc[e] += s; }
+        else if (g_Y != nullptr) g_Y[e * L + (v - 1)] += s;
+      });
     }
   }
   if (act) stv<V>(g_qk + (size_t)i * ldgqk + c, gq);
@@ -582,7 +584,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                         const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax,
                         int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe, int ldgz, float* da,
-                        float* gze_amax, cudaStream_t st, bool* handled);
+                        float* gze_amax, float* g_fc, float* g_Y, cudaStream_t st, bool* handled);
 int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                         const float* alpha, const float* da, const int32_t* src_ptr, const int32_t* src_perm,
@@ -673,10 +675,10 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
   if (gata_check(C, H, lmax, V)) return 1;
   if (N == 0) return 0;
   cudaStream_t st = as_stream(stream);
-  if (use_staged() && g_fc == nullptr && g_Y == nullptr) {  // geometry gradients (forces) stay on the kernels below
+  if (use_staged()) {
     bool handled = false;
     if (gata_bwd_tgt_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H, lmax,
-                            flags, max_deg_in, g_qk, ldgqk, gZe, ldgz, da, gze_amax, st, &handled))
+                            flags, max_deg_in, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y, st, &handled))
       return 1;
     if (handled) return 0;
   }
@@ -685,7 +687,9 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
   GOTEN_REQUIRE(g_cols % V == 0 && C % g_cols == 0, "unsupported head / channel combination (C=%d H=%d S=%d)", C, H, S);
   const int nparts = S * (C / g_cols);
   if (max_deg_in < 1) max_deg_in = 1;
-  const size_t smem = gata_smem_floats(max_deg_in, nparts, H, L, true) * sizeof(float);
+  const bool geo = g_fc != nullptr || g_Y != nullptr;
+  const int block_t = gata_block(C, V);
+  const size_t smem = (gata_smem_floats(max_deg_in, nparts, H, L, true) + (geo ? gata_geo_floats(block_t, L) : 0)) * sizeof(float);
   GOTEN_REQUIRE(smem <= 200 * 1024, "max in-degree %d needs %zu B of shared memory", max_deg_in, smem);
   GATA_DISPATCH(gata_bwd_tgt_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr,
                 src, N, C, H, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, g_fc, g_Y, gze_amax);

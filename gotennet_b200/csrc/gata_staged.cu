@@ -225,16 +225,18 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
 //   softmax backward (gotennet.py:503-511)  -> da[e][hd] (also consumed by the source pass);
 //   pass B (plain loads, 2 KB/edge): dq_i and d(pre-activation of W_re) -> gZe[e, 0:C].
 // smem tail: part[max_deg][S][n_grp] | al[max_deg][H] | aux[max_deg][H]
-template <int LMAX, bool SD, bool ST>
-__global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const float* __restrict__ g_Xd,
-                                           const float* __restrict__ Xd, const float* __restrict__ qk, int ldqk,
-                                           const float* __restrict__ x, const float* __restrict__ v,
-                                           const float* __restrict__ Ze, int ldz, const float* __restrict__ Y,
-                                           const float* __restrict__ fc, const float* __restrict__ kappa,
-                                           const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
-                                           const int32_t* __restrict__ src, int N, int C, int H, int R, int max_deg,
-                                           int g_cols, float* __restrict__ g_qk, int ldgqk, float* __restrict__ gZe,
-                                           int ldgz, float* __restrict__ da_out, float* __restrict__ gze_amax) {
+// GEO: also the geometry gradients (forces): g_fc[e] += sum_c dout . (filter x_j) and g_Y[e][m] += sum_c o_d . gX_i[m]
+// (o_d = the forward message of the direction chunk), reduced over the block with one extra barrier per edge; the
+// filter row of the edge is read straight from Ze (it is used once, by one thread).
+template <int LMAX, bool SD, bool ST, bool GEO>
+__device__ __forceinline__ void gata_bwd_tgt_staged_body(
+    const float* __restrict__ g_h, const float* __restrict__ g_Xd, const float* __restrict__ Xd,
+    const float* __restrict__ qk, int ldqk, const float* __restrict__ x, const float* __restrict__ v,
+    const float* __restrict__ Ze, int ldz, const float* __restrict__ Y, const float* __restrict__ fc,
+    const float* __restrict__ kappa, const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
+    const int32_t* __restrict__ src, int N, int C, int H, int R, int max_deg, int g_cols, float* __restrict__ g_qk,
+    int ldgqk, float* __restrict__ gZe, int ldgz, float* __restrict__ da_out, float* __restrict__ gze_amax,
+    float* __restrict__ g_fc, float* __restrict__ g_Y) {
   using Cf = Cfg<LMAX, SD, ST>;
   float amx = 0.f;
   constexpr int L = Cf::L, S = Cf::S, ND = Cf::ND;
@@ -256,6 +258,7 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
   float* s_aux = s_al + (size_t)max_deg * H;            // [max_deg][H]
   // [2][S][blockDim]: per-thread d alpha~ partials of one edge (16 B aligned for the vector group sums)
   float* s_pk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_aux + (size_t)max_deg * H) + 15) & ~uintptr_t(15));
+  float* s_geo = s_pk + (size_t)2 * S * blockDim.x;      // GEO: [2][(1 + L)][blockDim + 4]
   const uint32_t bar0 = tma::smem_u32(bars);
   const uint32_t stage0 = tma::smem_u32(stages);
 
@@ -266,6 +269,12 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
   if (tid == 0) {
     for (int s = 0; s < R; ++s) tma::mbar_init(bar0 + 8 * s, 1);
     tma::fence_barrier_init();
+  }
+  int hd_of[S];
+#pragma unroll
+  for (int k = 0; k < S; ++k) hd_of[k] = act ? (k * C + c) / SD_ : 0;
+  if (GEO) {  // attention weights of every edge of this target (pass A needs alpha~ = alpha * kappa)
+    for (int idx = tid; idx < deg * H; idx += blockDim.x) s_al[idx] = alpha[(size_t)e0 * H + idx];
   }
   float4 gh = make_float4(0.f, 0.f, 0.f, 0.f), gX[L];
 #pragma unroll
@@ -304,6 +313,9 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
       float pk[S];
 #pragma unroll
       for (int k = 0; k < S; ++k) pk[k] = 0.f;
+      float geo[1 + L];  // GEO: [d fc | d Y_m] partials of this thread
+#pragma unroll
+      for (int m = 0; m <= L; ++m) geo[m] = 0.f;
       if (act) {
         tma::mbar_wait(bar0 + 8 * s, (uint32_t)((gt / R) & 1));
         const float4* st = reinterpret_cast<const float4*>(stages + (size_t)s * stage_floats);
@@ -323,6 +335,8 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
           }
         }
         float* gz = gZe + (size_t)(e0 + gt) * ldgz + C + c;
+        float4 od[ND];  // GEO: forward messages of the direction chunks (gotennet.py:522-526, 532)
+        const float kap = GEO ? kappa[e0 + gt] : 0.f;
 #pragma unroll
         for (int k = 0; k < S; ++k) {
           const float4 vv = st[(L + k) * C4 + tid], xv = st[(L + S + k) * C4 + tid];
@@ -330,7 +344,34 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
           const float4 gv = make_float4(dout[k].x * xv.x * f, dout[k].y * xv.y * f, dout[k].z * xv.z * f, dout[k].w * xv.w * f);
           amx = amax4(amx, gv.x, gv.y, gv.z, gv.w);
           st4(gz + k * C, gv);
+          if (GEO) {
+            const float4 tf = ld4(Ze + (size_t)(e0 + gt) * ldz + C + k * C + c);
+            const float4 sx = make_float4(tf.x * xv.x, tf.y * xv.y, tf.z * xv.z, tf.w * xv.w);
+            geo[0] += dout[k].x * sx.x + dout[k].y * sx.y + dout[k].z * sx.z + dout[k].w * sx.w;
+            if (k >= 1 && k <= ND) {
+              const float al = s_al[gt * H + hd_of[k]] * kap;
+              od[k - 1] = make_float4(fmaf(sx.x, f, al * vv.x), fmaf(sx.y, f, al * vv.y), fmaf(sx.z, f, al * vv.z),
+                                      fmaf(sx.w, f, al * vv.w));
+            }
+          }
         }
+        if (GEO) {
+#pragma unroll
+          for (int l = 0; l < LMAX; ++l) {
+#pragma unroll
+            for (int m = lo_of(l); m < hi_of(l); ++m) {
+              const float4 o4 = od[SD ? l : 0];
+              geo[1 + m] = o4.x * gX[m].x + o4.y * gX[m].y + o4.z * gX[m].z + o4.w * gX[m].w;
+            }
+          }
+        }
+      }
+      if (GEO) {  // block-uniform: 1 + L channel sums of this edge
+        const size_t e = (size_t)(e0 + gt);
+        block_sums_one_barrier<1 + L>(geo, s_geo + (size_t)(gt & 1) * (1 + L) * (blockDim.x + 4), [&](int vi, float sum) {
+          if (vi == 0) { if (g_fc != nullptr) g_fc[e] += sum; }
+          else if (g_Y != nullptr) g_Y[e * L + (vi - 1)] += sum;
+        });
       }
       // group sums of the partials (gt_ consecutive threads, never across a warp): every thread stores its S values,
       // then S * n_grp threads each add one group's gt_ values (conflict-free smem reads instead of S log2(gt_)
@@ -422,6 +463,28 @@ __global__ void gata_bwd_tgt_staged_kernel(const float* __restrict__ g_h, const 
   st4(g_qk + (size_t)i * ldgqk + c, gq);
   amax_commit(gze_amax, amx);
 }
+
+#define GOTEN_BWD_TGT_ARGS                                                                                            \
+  const float *__restrict__ g_h, const float *__restrict__ g_Xd, const float *__restrict__ Xd,                       \
+      const float *__restrict__ qk, int ldqk, const float *__restrict__ x, const float *__restrict__ v,              \
+      const float *__restrict__ Ze, int ldz, const float *__restrict__ Y, const float *__restrict__ fc,              \
+      const float *__restrict__ kappa, const float *__restrict__ alpha, const int32_t *__restrict__ tgt_ptr,         \
+      const int32_t *__restrict__ src, int N, int C, int H, int R, int max_deg, int g_cols, float *__restrict__ g_qk, \
+      int ldgqk, float *__restrict__ gZe, int ldgz, float *__restrict__ da_out, float *__restrict__ gze_amax,        \
+      float *__restrict__ g_fc, float *__restrict__ g_Y
+#define GOTEN_BWD_TGT_PASS                                                                                          \
+  g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H, R, max_deg, g_cols, g_qk, ldgqk, \
+      gZe, ldgz, da_out, gze_amax, g_fc, g_Y
+template <int LMAX, bool SD, bool ST>
+__global__ void gata_bwd_tgt_staged_kernel(GOTEN_BWD_TGT_ARGS) {
+  gata_bwd_tgt_staged_body<LMAX, SD, ST, false>(GOTEN_BWD_TGT_PASS);
+}
+template <int LMAX, bool SD, bool ST>
+__global__ void gata_bwd_tgt_staged_geo_kernel(GOTEN_BWD_TGT_ARGS) {
+  gata_bwd_tgt_staged_body<LMAX, SD, ST, true>(GOTEN_BWD_TGT_PASS);
+}
+#undef GOTEN_BWD_TGT_ARGS
+#undef GOTEN_BWD_TGT_PASS
 
 // --------------------------------------------------------- backward, source ---
 // Per source j over the transposed view.  Stage layout (floats):
@@ -670,7 +733,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
                         const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax,
                         int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe, int ldgz, float* da,
-                        float* gze_amax, cudaStream_t st, bool* handled) {
+                        float* gze_amax, float* g_fc, float* g_Y, cudaStream_t st, bool* handled) {
   *handled = false;
   const int D = C / H;
   if (C % 4 != 0 || D % 4 != 0 || ldqk % 4 != 0 || ldz % 4 != 0 || ldgqk % 4 != 0 || ldgz % 4 != 0) return 0;
@@ -687,13 +750,18 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   if (max_deg_in < 1) max_deg_in = 1;
   int R = staged::ring_depth();
   const size_t stage_bytes = (size_t)(2 * S + L) * C * 4;
+  const bool geo = g_fc != nullptr || g_Y != nullptr;
   const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (2 + L) * 4 + (size_t)max_deg_in * (S * n_grp + 2 * H) * 4 +
-                      (size_t)2 * S * block * 4 + 16;
+                      (size_t)2 * S * block * 4 + 16 + (geo ? (size_t)2 * (1 + L) * (block + 4) * 4 : 0);
   while (R > 1 && R * stage_bytes + tail > 220 * 1024) --R;
   const size_t smem = R * stage_bytes + tail;
   if (R * stage_bytes + tail > 220 * 1024) return 0;
-  STAGED_DISPATCH(gata_bwd_tgt_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha,
-                  tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax);
+  if (geo)
+    STAGED_DISPATCH(gata_bwd_tgt_staged_geo_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa,
+                    alpha, tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y);
+  else
+    STAGED_DISPATCH(gata_bwd_tgt_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha,
+                    tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
   return 0;

@@ -153,6 +153,7 @@ __device__ __forceinline__ void col_of(const float (*a)[V], int q, float* out) {
 // neighbour-row gathers of consecutive edges are independent and overlap.  Used by the target half of the backward
 // (measured on B200, C = 256: 1.49 -> 1.35 ms per step); the forward and the source half are faster without it.
 constexpr int EC = 32;
+constexpr int GY_MAX_BLOCK = 256;  // largest block of the force-gradient instantiation (static scratch)
 template <int L>
 struct EdgeMeta {
   int nbr[EC];
@@ -228,7 +229,8 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
                                                  float* __restrict__ gze_amax, float* __restrict__ geq_amax) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   __shared__ EdgeMeta<L> sm;
-  __shared__ float red[33];
+  // geometry gradient: per-edge channel sums of gy[L] through block_sums_one_barrier (blocks of <= GY_MAX_BLOCK threads)
+  __shared__ float gy_scratch[GY ? 2 * L * (GY_MAX_BLOCK + 4) : 1];
   const int i = blockIdx.x, c = threadIdx.x * V;
   const bool act = c < C;
   float amx = 0.f;
@@ -285,12 +287,9 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
         }
         stv<V>(gZe + (size_t)e * ldgz + zt_col0 + c, gz);
       }
-      if (GY) {  // geometry gradient for forces (block-uniform)
-#pragma unroll
-        for (int m = 0; m < L; ++m) {
-          const float sgy = block_sum(gy[m], red);
-          if (threadIdx.x == 0) g_Y[(size_t)e * L + m] += sgy;
-        }
+      if (GY) {  // geometry gradient for forces (block-uniform): L channel sums, one barrier
+        block_sums_one_barrier<L>(gy, gy_scratch + (size_t)(u & 1) * L * (blockDim.x + 4),
+                                  [&](int m, float sgy) { g_Y[(size_t)e * L + m] += sgy; });
       }
     }
   }
@@ -431,6 +430,12 @@ int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, con
 int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                       int zt_col0, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
                       float* g_EQ, float* gZe, int ldgz, float* g_Y, float* gze_amax, float* geq_amax, void* stream) {
+  if (g_Y != nullptr) {
+    GOTEN_REQUIRE(block_for(C, htr_vec(4)) <= GY_MAX_BLOCK,
+                  "n_atom_basis=%d too wide for the force-gradient HTR kernel (block <= %d threads)", C, GY_MAX_BLOCK);
+    GOTEN_REQUIRE(C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0,
+                  "the force-gradient HTR kernel needs 16-byte aligned rows (C=%d)", C);
+  }
   if (g_Y != nullptr)
     HTR_DISPATCH(htr_bwd_tgt_gy_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
                  g_Y, gze_amax, geq_amax);

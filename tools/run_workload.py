@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--batch", type=int, default=None)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--profile", action="store_true", help="per-entry-point CUDA-event table of one extra step (stderr)")
     args = ap.parse_args()
     import gotennet_b200 as g
     from gotennet_b200._lib import lib
@@ -79,6 +80,18 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
+    if args.profile:
+        L.profile = []
+        step()
+        torch.cuda.synchronize()
+        prof, L.profile = L.profile, None
+        agg = {}
+        for name, a, p0, p1 in prof:
+            d = agg.setdefault(name, [0, 0.0])
+            d[0] += 1
+            d[1] += p0.elapsed_time(p1)
+        for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
+            print(f"  {name:30s} {cnt:4d}x {t:8.3f} ms {100 * t / ms:5.1f}%", file=sys.stderr)
     plan = model.last_plan
     finite = bool(torch.isfinite(loss).item()) and bool(torch.isfinite(gpos).all().item())
     print(json.dumps({
