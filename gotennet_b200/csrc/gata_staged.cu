@@ -224,7 +224,7 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
 //           gZe[e, C:(S+1)C], d alpha~ partials per (edge, chunk, column group) into smem;
 //   softmax backward (gotennet.py:503-511)  -> da[e][hd] (also consumed by the source pass);
 //   pass B (plain loads, 2 KB/edge): dq_i and d(pre-activation of W_re) -> gZe[e, 0:C].
-// smem tail: part[max_deg][S][n_grp] | al[max_deg][H] | aux[max_deg][H]
+// smem tail: part[EC][S][n_grp] (one chunk of edges) | al[max_deg][H] | aux[max_deg][H]
 // GEO: also the geometry gradients (forces): g_fc[e] += sum_c dout . (filter x_j) and g_Y[e][m] += sum_c o_d . gX_i[m]
 // (o_d = the forward message of the direction chunk), reduced over the block with one extra barrier per edge; the
 // filter row of the edge is read straight from Ze (it is used once, by one thread).
@@ -253,8 +253,8 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
   int* s_src = reinterpret_cast<int*>(bars + 8);  // 8 barrier slots (R <= 8)
   float* s_fc = reinterpret_cast<float*>(s_src + EC);
   float* s_Y = s_fc + EC;                               // [EC][L]
-  float* part = s_Y + EC * L;                           // [max_deg][S][n_grp]
-  float* s_al = part + (size_t)max_deg * S * n_grp;     // [max_deg][H]
+  float* part = s_Y + EC * L;                           // [EC][S][n_grp]: group sums of the current chunk of edges
+  float* s_al = part + (size_t)EC * S * n_grp;          // [max_deg][H]
   float* s_aux = s_al + (size_t)max_deg * H;            // [max_deg][H]
   // [2][S][blockDim]: per-thread d alpha~ partials of one edge (16 B aligned for the vector group sums)
   float* s_pk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_aux + (size_t)max_deg * H) + 15) & ~uintptr_t(15));
@@ -394,21 +394,25 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
         } else {
           for (int u = 0; u < gt_; ++u) p += pp[u];
         }
-        part[(size_t)gt * S * n_grp + o] = p;
+        part[(size_t)t * S * n_grp + o] = p;
       }
       if (tid == 0 && t + R < n) issue(gt + R, t + R);
     }
+    // ---- chunk epilogue: d alpha~[e][hd] = kappa_e * sum of the group sums whose columns lie in head hd
+    // (per chunk, so `part` holds EC edges whatever the in-degree: 160-neighbour molecules keep 4 CTAs per SM)
+    __syncthreads();
+    for (int idx = tid; idx < n * H; idx += blockDim.x) {
+      const int t = idx / H, hd = idx - t * H;
+      float sacc = 0.f;
+      for (int k = 0; k < S; ++k)
+        for (int g = 0; g < n_grp; ++g)
+          if ((k * C + g * g_cols) / SD_ == hd) sacc += part[((size_t)t * S + k) * n_grp + g];
+      s_aux[(size_t)(c0 + t) * H + hd] = sacc * kappa[e0 + c0 + t];
+    }
   }
   __syncthreads();
-  // ---- d alpha[e][hd] = kappa_e * sum of the partials whose column group lies in head hd
-  for (int idx = tid; idx < deg * H; idx += blockDim.x) {
-    const int t = idx / H, hd = idx - t * H;
-    float sacc = 0.f;
-    for (int k = 0; k < S; ++k)
-      for (int g = 0; g < n_grp; ++g)
-        if ((k * C + g * g_cols) / SD_ == hd) sacc += part[((size_t)t * S + k) * n_grp + g];
-    s_aux[idx] = sacc * kappa[e0 + t];
-    s_al[idx] = alpha[(size_t)e0 * H + idx];
+  if (!GEO) {
+    for (int idx = tid; idx < deg * H; idx += blockDim.x) s_al[idx] = alpha[(size_t)e0 * H + idx];
   }
   __syncthreads();
   // ---- softmax backward: da = alpha * (dalpha - sum_e alpha dalpha)
@@ -751,7 +755,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   int R = staged::ring_depth();
   const size_t stage_bytes = (size_t)(2 * S + L) * C * 4;
   const bool geo = g_fc != nullptr || g_Y != nullptr;
-  const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (2 + L) * 4 + (size_t)max_deg_in * (S * n_grp + 2 * H) * 4 +
+  const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (2 + L + S * n_grp) * 4 + (size_t)max_deg_in * 2 * H * 4 +
                       (size_t)2 * S * block * 4 + 16 + (geo ? (size_t)2 * (1 + L) * (block + 4) * 4 : 0);
   while (R > 1 && R * stage_bytes + tail > 220 * 1024) --R;
   const size_t smem = R * stage_bytes + tail;

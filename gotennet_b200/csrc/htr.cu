@@ -431,15 +431,16 @@ int goten_htr_bwd_tgt(const float* g_t_out, const float* EQ, const float* EK, in
                       int zt_col0, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int lmax, int flags,
                       float* g_EQ, float* gZe, int ldgz, float* g_Y, float* gze_amax, float* geq_amax, void* stream) {
   if (g_Y != nullptr) {
-    GOTEN_REQUIRE(block_for(C, htr_vec(4)) <= GY_MAX_BLOCK,
+    GOTEN_REQUIRE(block_for(C, htr_vec(lmax >= 3 ? 2 : 4)) <= GY_MAX_BLOCK,
                   "n_atom_basis=%d too wide for the force-gradient HTR kernel (block <= %d threads)", C, GY_MAX_BLOCK);
     GOTEN_REQUIRE(C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0,
                   "the force-gradient HTR kernel needs 16-byte aligned rows (C=%d)", C);
   }
   if (g_Y != nullptr)
-    HTR_DISPATCH(htr_bwd_tgt_gy_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
+    HTR_DISPATCH(htr_bwd_tgt_gy_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), (lmax >= 3 ? 2 : 4), g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
                  g_Y, gze_amax, geq_amax);
-  HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), 4, g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
+  // lmax = 3: 2 x 15 x V accumulators per thread; two channels per thread keep them in registers
+  HTR_DISPATCH(htr_bwd_tgt_kernel, (C % 4 == 0 && ldp % 4 == 0 && ldz % 4 == 0 && zt_col0 % 4 == 0 && ldgz % 4 == 0), (lmax >= 3 ? 2 : 4), g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz,
                g_Y, gze_amax, geq_amax);
 }
 
