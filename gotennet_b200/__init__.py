@@ -14,3 +14,4 @@ from .layers import CosineCutoff, Dense, Distance, ExpNormalSmearing, MLP, Tenso
 from .outputs import Atomwise, ScaleShift, SchnetMLP, shifted_softplus  # noqa: F401
 from .optim import FusedAdamW  # noqa: F401
 from .parallel import FlatGradBuffer, shard_bounds, take_shard  # noqa: F401
+from .data import MoleculeBatch, collate  # noqa: F401

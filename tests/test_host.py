@@ -97,3 +97,49 @@ def test_scalar_utilities_match_oracle(g):
     u = torch.nn.functional.normalize(torch.randn(20, 3), dim=1)
     for l in (1, 2, 3):
         assert torch.allclose(g.TensorInit(l)(u), orc.sph_harm(l, u))
+
+
+def test_flat_grad_buffer_layout():
+    """FlatGradBuffer: every tensor starts on a 16-byte boundary, views alias the flat storage, padding stays zero,
+    pack() copies present gradients and zero-fills missing ones (host logic, CPU tensors)."""
+    from gotennet_b200.parallel import FlatGradBuffer
+    ps = [torch.nn.Parameter(torch.randn(*s)) for s in [(7, 5), (33,), (3,), (64, 64)]]
+    frozen = torch.nn.Parameter(torch.randn(5), requires_grad=False)
+    fb = FlatGradBuffer(ps + [frozen])
+    assert len(fb.params) == 4 and all(o % 4 == 0 for o in fb.offsets) and fb.numel % 4 == 0
+    assert fb.numel == 36 + 36 + 4 + 4096
+    for p in ps[:3]:
+        p.grad = torch.ones_like(p)
+    flat = fb.pack()
+    assert flat.data_ptr() == fb.flat.data_ptr()
+    for o, n, v, p in zip(fb.offsets, fb.sizes, fb.views, ps):
+        assert v.data_ptr() == fb.flat.data_ptr() + 4 * o and v.shape == p.shape
+        expect = 1.0 if p.grad is not None else 0.0
+        assert torch.all(flat[o:o + n] == expect)
+    assert float(flat[35]) == 0.0 and float(flat[36 + 33]) == 0.0      # padding
+    fb.unpack()
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(ps, fb.views))
+
+
+def test_amax_scope_inert_without_fp16_arm(monkeypatch):
+    """AmaxScope never touches the device when the split-fp16 arm is disabled (GOTEN_GEMM=simt / GOTEN_TC16=0)."""
+    from gotennet_b200 import ops
+    monkeypatch.setenv("GOTEN_GEMM", "simt")
+    sc = ops.AmaxScope()
+    assert not sc.enabled and sc.export([torch.zeros(3)]) == []
+    monkeypatch.setenv("GOTEN_GEMM", "auto")
+    monkeypatch.setenv("GOTEN_TC16", "0")
+    assert not ops.AmaxScope().enabled
+    monkeypatch.delenv("GOTEN_TC16")
+    assert ops.AmaxScope().enabled
+
+
+def test_collate_ragged_molecules(g):
+    mols = [([1, 6, 8], [[0, 0, 0], [1, 0, 0], [0, 1, 0]]), ([6], [[5.0, 5.0, 5.0]]), ([], []), ([7, 7], [[0, 0, 1], [0, 0, 2]])]
+    b = g.collate(mols)
+    assert b.num_graphs == 4 and b.z.tolist() == [1, 6, 8, 6, 7, 7] and b.pos.shape == (6, 3)
+    assert b.batch.tolist() == [0, 0, 0, 1, 3, 3] and b.ptr.tolist() == [0, 3, 4, 4, 6]
+    assert b["pos"] is b.pos and b.pos.dtype == torch.float32 and b.z.dtype == torch.int64
+    with pytest.raises(ValueError):
+        g.collate([([1, 1], [[0, 0, 0]])])
+    assert g.collate([]).num_graphs == 0
