@@ -5,8 +5,9 @@ bench.py keeps the contract workload, configs[1]).
     python tools/run_workload.py md22  [--batch 64]   [--steps 5]     # configs[3]: 370 atoms, lmax=3, K=160
     python tools/run_workload.py qm9   [--batch 1024]
 
-A step = radius graph + geometry + forward + backward (all parameter gradients and d/d pos).  For rmd17 the loss is the
-summed Atomwise energy, so pos.grad is minus the forces (first-order; outputs.py:365-375).  Prints one JSON line.
+A step = radius graph + geometry + forward + backward (all parameter gradients).  For rmd17 the loss is the summed
+Atomwise energy and positions require grad, so pos.grad is minus the forces (first-order; outputs.py:365-375).
+Prints one JSON line.
 """
 import argparse
 import json
@@ -55,7 +56,7 @@ def main():
 
     def step():
         d = Data()
-        d.z, d.pos, d.batch = zd, pd.clone().requires_grad_(True), bd
+        d.z, d.pos, d.batch = zd, (pd.clone().requires_grad_(True) if head is not None else pd), bd
         d.num_graphs = B
         for p in params:
             p.grad = None
@@ -93,7 +94,7 @@ def main():
         for name, (cnt, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:14]:
             print(f"  {name:30s} {cnt:4d}x {t:8.3f} ms {100 * t / ms:5.1f}%", file=sys.stderr)
     plan = model.last_plan
-    finite = bool(torch.isfinite(loss).item()) and bool(torch.isfinite(gpos).all().item())
+    finite = bool(torch.isfinite(loss).item()) and (gpos is None or bool(torch.isfinite(gpos).all().item()))
     print(json.dumps({
         "workload": args.workload, "molecules": B, "atoms": plan.N, "edges": plan.E, "max_in_degree": plan.max_deg_in,
         "model": {**BASE, **w["model"]}, "max_num_neighbors": w["max_nbr"], "force_head": w["head"],
