@@ -114,7 +114,7 @@ template <int LMAX, bool SD, bool ST, int V>
 __global__ void gata_fwd_kernel(const float* __restrict__ h, const float* __restrict__ Xd, const float* __restrict__ qk,
                                 int ldqk, const float* __restrict__ x, const float* __restrict__ v,
                                 const float* __restrict__ Ze, int ldz, const float* __restrict__ Y,
-                                const float* __restrict__ fc, const float* __restrict__ kappa,
+                                const float* __restrict__ fc, const float* __restrict__ kappa, const float* __restrict__ drop,
                                 const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C, int H,
                                 int max_deg, float* __restrict__ h_out, float* __restrict__ Xd_out, float* __restrict__ xd_amax,
                                 float* __restrict__ alpha_out) {
@@ -181,8 +181,9 @@ __global__ void gata_fwd_kernel(const float* __restrict__ h, const float* __rest
       const float den = sum + 1e-16f;
       for (int t = lane; t < deg; t += 32) {
         const float al = sm.alpha[t * H + hd] / den;
-        sm.alpha[t * H + hd] = al;
         alpha_out[(size_t)(e0 + t) * H + hd] = al;
+        // attention dropout (gotennet.py:513): `drop` = mask / (1 - p) per (edge, head); the messages use the dropped weights
+        sm.alpha[t * H + hd] = drop ? al * drop[(size_t)(e0 + t) * H + hd] : al;
       }
     }
   }
@@ -261,7 +262,7 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
                                     const float* __restrict__ Xd, const float* __restrict__ qk, int ldqk,
                                     const float* __restrict__ x, const float* __restrict__ v,
                                     const float* __restrict__ Ze, int ldz, const float* __restrict__ Y,
-                                    const float* __restrict__ fc, const float* __restrict__ kappa,
+                                    const float* __restrict__ fc, const float* __restrict__ kappa, const float* __restrict__ drop,
                                     const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
                                     const int32_t* __restrict__ src, int N, int C, int H, int max_deg, int g_cols,
                                     float* __restrict__ g_qk, int ldgqk, float* __restrict__ gZe, int ldgz,
@@ -338,7 +339,7 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
     for (int k = 0; k < S; ++k)
       for (int g = 0; g < n_grp; ++g)
         if ((k * C + g * g_cols) / SD_ == hd) s += sm.part[(t * S + k) * n_grp + g];
-    sm.aux[idx] = s * sm.kap[t];  // alpha~ = alpha * kappa
+    sm.aux[idx] = s * sm.kap[t] * (drop ? drop[(size_t)(e0 + t) * H + hd] : 1.0f);  // alpha~ = alpha * kappa * dropout
   }
   __syncthreads();
   // ---- softmax backward: da = alpha * (dalpha - sum_e alpha dalpha)
@@ -400,7 +401,7 @@ __global__ void gata_bwd_tgt_kernel(const float* __restrict__ g_h, const float* 
           float tf[V], vv[V];
           ldv<V>(Ze + e * ldz + C + col, tf);
           ldv<V>(v + (size_t)j * SC + col, vv);
-          const float al = sm.alpha[t * H + hd_of[k]] * sm.kap[t];
+          const float al = sm.alpha[t * H + hd_of[k]] * sm.kap[t] * (drop ? drop[e * H + hd_of[k]] : 1.0f);
 #pragma unroll
           for (int q = 0; q < V; ++q) {
             gfc_part = fmaf(dout[k][q], tf[q] * xv[q], gfc_part);
@@ -443,7 +444,7 @@ __global__ void gata_bwd_src_kernel(const float* __restrict__ g_h, const float* 
                                     const float* __restrict__ Xd, const float* __restrict__ qk, int ldqk,
                                     const float* __restrict__ x, const float* __restrict__ v,
                                     const float* __restrict__ Ze, int ldz, const float* __restrict__ Y,
-                                    const float* __restrict__ fc, const float* __restrict__ kappa,
+                                    const float* __restrict__ fc, const float* __restrict__ kappa, const float* __restrict__ drop,
                                     const float* __restrict__ alpha, const float* __restrict__ da,
                                     const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src_perm,
                                     const int32_t* __restrict__ tgt, int N, int C, int H, float* __restrict__ g_qk,
@@ -495,7 +496,8 @@ __global__ void gata_bwd_src_kernel(const float* __restrict__ g_h, const float* 
     for (int q = threadIdx.x; q < n * L; q += blockDim.x) s_Y[q] = Y[(size_t)s_e[q / L] * L + (q % L)];
     for (int q = threadIdx.x; q < n * H; q += blockDim.x) {
       const size_t o_ = (size_t)s_e[q / H] * H + (q % H);
-      s_al[q] = alpha[o_]; s_da[q] = da[o_];
+      s_al[q] = drop ? alpha[o_] * drop[o_] : alpha[o_];
+      s_da[q] = da[o_];
     }
     __syncthreads();
     if (act) {
@@ -575,18 +577,18 @@ static int gata_check(int C, int H, int lmax, int V) {
 
 // TMA-staged production variants (gata_staged.cu); *handled = false -> shape outside their contract
 int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, const float* x, const float* v,
-                    const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                    const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                     const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax, int flags,
                     int max_deg_in, float* h_out, float* Xd_out, float* alpha, float* xd_amax, cudaStream_t st,
                     bool* handled);
 
 int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
-                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                         const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax,
                         int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe, int ldgz, float* da,
                         float* gze_amax, float* g_fc, float* g_Y, cudaStream_t st, bool* handled);
 int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
-                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                         const float* alpha, const float* da, const int32_t* src_ptr, const int32_t* src_perm,
                         const int32_t* tgt, int N, int C, int H, int lmax, int flags, float* g_qk, int ldgqk, float* g_x,
                         float* g_v, float* g_Xd_in, cudaStream_t st, bool* handled);
@@ -642,7 +644,7 @@ static inline int multiplier_of(int lmax, int flags) {
 extern "C" {
 
 int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, const float* x, const float* v,
-                   const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                   const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                    const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax, int flags,
                    int max_deg_in, float* h_out, float* Xd_out, float* alpha, float* xd_amax, void* stream) {
   const int V = gata_vec(C, H, ldqk, ldz);
@@ -651,7 +653,7 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
   cudaStream_t st = as_stream(stream);
   if (use_staged()) {
     bool handled = false;
-    if (gata_fwd_staged(h, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, tgt_ptr, src, N, C, H, lmax, flags, max_deg_in,
+    if (gata_fwd_staged(h, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, tgt_ptr, src, N, C, H, lmax, flags, max_deg_in,
                         h_out, Xd_out, alpha, xd_amax, st, &handled))
       return 1;
     if (handled) return 0;
@@ -660,7 +662,7 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
   if (max_deg_in < 1) max_deg_in = 1;
   const size_t smem = gata_smem_floats(max_deg_in, nparts, H, L, false) * sizeof(float);
   GOTEN_REQUIRE(smem <= 200 * 1024, "max in-degree %d needs %zu B of shared memory", max_deg_in, smem);
-  GATA_DISPATCH(gata_fwd_kernel, N, smem, h, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, tgt_ptr, src, N, C, H,
+  GATA_DISPATCH(gata_fwd_kernel, N, smem, h, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, tgt_ptr, src, N, C, H,
                 max_deg_in, h_out, Xd_out, xd_amax, alpha);
   GOTEN_CHECK_LAUNCH();
   return 0;
@@ -668,7 +670,7 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
 
 int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk,
                        const float* x, const float* v, const float* Ze, int ldz, const float* Y, const float* fc,
-                       const float* kappa, const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N,
+                       const float* kappa, const float* drop, const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N,
                        int C, int H, int lmax, int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe,
                        int ldgz, float* da, float* g_fc, float* g_Y, float* gze_amax, void* stream) {
   const int V = (gata_vec(C, H, ldqk, ldz) == 4 && ldgqk % 4 == 0 && ldgz % 4 == 0) ? 4 : 1;
@@ -677,7 +679,7 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
   cudaStream_t st = as_stream(stream);
   if (use_staged()) {
     bool handled = false;
-    if (gata_bwd_tgt_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H, lmax,
+    if (gata_bwd_tgt_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, tgt_ptr, src, N, C, H, lmax,
                             flags, max_deg_in, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y, st, &handled))
       return 1;
     if (handled) return 0;
@@ -691,7 +693,7 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
   const int block_t = gata_block(C, V);
   const size_t smem = (gata_smem_floats(max_deg_in, nparts, H, L, true) + (geo ? gata_geo_floats(block_t, L) : 0)) * sizeof(float);
   GOTEN_REQUIRE(smem <= 200 * 1024, "max in-degree %d needs %zu B of shared memory", max_deg_in, smem);
-  GATA_DISPATCH(gata_bwd_tgt_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr,
+  GATA_DISPATCH(gata_bwd_tgt_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, tgt_ptr,
                 src, N, C, H, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, g_fc, g_Y, gze_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
@@ -699,7 +701,7 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
 
 int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk,
                        const float* x, const float* v, const float* Ze, int ldz, const float* Y, const float* fc,
-                       const float* kappa, const float* alpha, const float* da, const int32_t* src_ptr,
+                       const float* kappa, const float* drop, const float* alpha, const float* da, const int32_t* src_ptr,
                        const int32_t* src_perm, const int32_t* tgt, int N, int C, int H, int lmax, int flags,
                        float* g_qk, int ldgqk, float* g_x, float* g_v, float* g_Xd_in, void* stream) {
   const int V = (gata_vec(C, H, ldqk, ldz) == 4 && ldgqk % 4 == 0) ? 4 : 1;
@@ -708,14 +710,14 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
   cudaStream_t st = as_stream(stream);
   if (use_staged()) {
     bool handled = false;
-    if (gata_bwd_src_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, da, src_ptr, src_perm, tgt, N, C,
+    if (gata_bwd_src_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, da, src_ptr, src_perm, tgt, N, C,
                             H, lmax, flags, g_qk, ldgqk, g_x, g_v, g_Xd_in, st, &handled))
       return 1;
     if (handled) return 0;
   }
   const int L = (lmax + 1) * (lmax + 1) - 1;
   const size_t smem = (size_t)SRC_CHUNK * (4 + L + 2 * H) * sizeof(float);
-  GATA_DISPATCH(gata_bwd_src_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, da,
+  GATA_DISPATCH(gata_bwd_src_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, da,
                 src_ptr, src_perm, tgt, N, C, H, g_qk, ldgqk, g_x, g_v, g_Xd_in);
   GOTEN_CHECK_LAUNCH();
   return 0;

@@ -109,7 +109,7 @@ template <int LMAX, bool SD, bool ST>
 __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __restrict__ Xd, const float* __restrict__ x,
                                     const float* __restrict__ v, const float* __restrict__ Ze, int ldz,
                                     const float* __restrict__ Y, const float* __restrict__ fc,
-                                    const float* __restrict__ kappa, const float* __restrict__ alpha,
+                                    const float* __restrict__ kappa, const float* __restrict__ drop, const float* __restrict__ alpha,
                                     const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
                                     int H, int R, float* __restrict__ h_out, float* __restrict__ Xd_out,
                                     float* __restrict__ xd_amax) {
@@ -166,7 +166,11 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
       s_src[t] = src[e0 + c0 + t]; s_fc[t] = fc[e0 + c0 + t]; s_kap[t] = kappa[e0 + c0 + t];
     }
     for (int t = tid; t < n * L; t += blockDim.x) s_Y[t] = Y[(size_t)(e0 + c0) * L + t];
-    for (int t = tid; t < n * H; t += blockDim.x) s_al[t] = alpha[(size_t)(e0 + c0) * H + t];
+    // attention dropout (gotennet.py:513): `drop` holds mask / (1 - p) per (edge, head); NULL = eval / p = 0
+    for (int t = tid; t < n * H; t += blockDim.x) {
+      const size_t o_ = (size_t)(e0 + c0) * H + t;
+      s_al[t] = drop ? alpha[o_] * drop[o_] : alpha[o_];
+    }
     __syncthreads();
     if (tid == 0) {
       const int pre = n < R ? n : R;
@@ -233,7 +237,7 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
     const float* __restrict__ g_h, const float* __restrict__ g_Xd, const float* __restrict__ Xd,
     const float* __restrict__ qk, int ldqk, const float* __restrict__ x, const float* __restrict__ v,
     const float* __restrict__ Ze, int ldz, const float* __restrict__ Y, const float* __restrict__ fc,
-    const float* __restrict__ kappa, const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
+    const float* __restrict__ kappa, const float* __restrict__ drop, const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
     const int32_t* __restrict__ src, int N, int C, int H, int R, int max_deg, int g_cols, float* __restrict__ g_qk,
     int ldgqk, float* __restrict__ gZe, int ldgz, float* __restrict__ da_out, float* __restrict__ gze_amax,
     float* __restrict__ g_fc, float* __restrict__ g_Y) {
@@ -349,7 +353,8 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
             const float4 sx = make_float4(tf.x * xv.x, tf.y * xv.y, tf.z * xv.z, tf.w * xv.w);
             geo[0] += dout[k].x * sx.x + dout[k].y * sx.y + dout[k].z * sx.z + dout[k].w * sx.w;
             if (k >= 1 && k <= ND) {
-              const float al = s_al[gt * H + hd_of[k]] * kap;
+              float al = s_al[gt * H + hd_of[k]] * kap;
+              if (drop) al *= drop[(size_t)(e0 + gt) * H + hd_of[k]];
               od[k - 1] = make_float4(fmaf(sx.x, f, al * vv.x), fmaf(sx.y, f, al * vv.y), fmaf(sx.z, f, al * vv.z),
                                       fmaf(sx.w, f, al * vv.w));
             }
@@ -407,7 +412,10 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
       for (int k = 0; k < S; ++k)
         for (int g = 0; g < n_grp; ++g)
           if ((k * C + g * g_cols) / SD_ == hd) sacc += part[((size_t)t * S + k) * n_grp + g];
-      s_aux[(size_t)(c0 + t) * H + hd] = sacc * kappa[e0 + c0 + t];
+      // d alpha = d alpha~ * kappa * (dropout mask / (1 - p)); the softmax backward below uses the un-dropped alpha
+      float dal_ = sacc * kappa[e0 + c0 + t];
+      if (drop) dal_ *= drop[(size_t)(e0 + c0 + t) * H + hd];
+      s_aux[(size_t)(c0 + t) * H + hd] = dal_;
     }
   }
   __syncthreads();
@@ -472,12 +480,12 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
   const float *__restrict__ g_h, const float *__restrict__ g_Xd, const float *__restrict__ Xd,                       \
       const float *__restrict__ qk, int ldqk, const float *__restrict__ x, const float *__restrict__ v,              \
       const float *__restrict__ Ze, int ldz, const float *__restrict__ Y, const float *__restrict__ fc,              \
-      const float *__restrict__ kappa, const float *__restrict__ alpha, const int32_t *__restrict__ tgt_ptr,         \
+      const float *__restrict__ kappa, const float *__restrict__ drop, const float *__restrict__ alpha, const int32_t *__restrict__ tgt_ptr,         \
       const int32_t *__restrict__ src, int N, int C, int H, int R, int max_deg, int g_cols, float *__restrict__ g_qk, \
       int ldgqk, float *__restrict__ gZe, int ldgz, float *__restrict__ da_out, float *__restrict__ gze_amax,        \
       float *__restrict__ g_fc, float *__restrict__ g_Y
 #define GOTEN_BWD_TGT_PASS                                                                                          \
-  g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H, R, max_deg, g_cols, g_qk, ldgqk, \
+  g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, tgt_ptr, src, N, C, H, R, max_deg, g_cols, g_qk, ldgqk, \
       gZe, ldgz, da_out, gze_amax, g_fc, g_Y
 template <int LMAX, bool SD, bool ST>
 __global__ void gata_bwd_tgt_staged_kernel(GOTEN_BWD_TGT_ARGS) {
@@ -499,7 +507,7 @@ __global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const 
                                            const float* __restrict__ Xd, const float* __restrict__ qk, int ldqk,
                                            const float* __restrict__ x, const float* __restrict__ v,
                                            const float* __restrict__ Ze, int ldz, const float* __restrict__ Y,
-                                           const float* __restrict__ fc, const float* __restrict__ kappa,
+                                           const float* __restrict__ fc, const float* __restrict__ kappa, const float* __restrict__ drop,
                                            const float* __restrict__ alpha, const float* __restrict__ da,
                                            const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src_perm,
                                            const int32_t* __restrict__ tgt, int N, int C, int H, int R,
@@ -576,7 +584,8 @@ __global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const 
     for (int q = tid; q < n * L; q += blockDim.x) s_Y[q] = Y[(size_t)s_e[q / L] * L + (q % L)];
     for (int q = tid; q < n * H; q += blockDim.x) {
       const size_t o_ = (size_t)s_e[q / H] * H + (q % H);
-      s_al[q] = alpha[o_]; s_da[q] = da[o_];
+      s_al[q] = drop ? alpha[o_] * drop[o_] : alpha[o_];  // the message used the dropped weights
+      s_da[q] = da[o_];
     }
     if (tid == 0) {
       const int pre = n < R ? n : R;
@@ -690,7 +699,7 @@ static inline int multiplier_of_(int lmax, int flags) {
 // Returns 0 on success with *handled = true when the staged path ran; *handled = false means the
 // shape is outside its contract (rows not 16 B aligned, head layout) and the caller uses gata.cu.
 int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, const float* x, const float* v,
-                    const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                    const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                     const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax, int flags,
                     int max_deg_in, float* h_out, float* Xd_out, float* alpha, float* xd_amax, cudaStream_t st,
                     bool* handled) {
@@ -724,7 +733,7 @@ int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, 
     kfn<<<N, block, smem_a, st>>>(qk, ldqk, Ze, ldz, tgt_ptr, src, C, H, max_deg_in, alpha);
     GOTEN_CHECK_LAUNCH();
   }
-  STAGED_DISPATCH(gata_msg_fwd_kernel, N, block, smem_m, h, Xd, x, v, Ze, ldz, Y, fc, kappa, alpha, tgt_ptr, src, N, C, H,
+  STAGED_DISPATCH(gata_msg_fwd_kernel, N, block, smem_m, h, Xd, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, tgt_ptr, src, N, C, H,
                   R, h_out, Xd_out, xd_amax);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
@@ -734,7 +743,7 @@ int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, 
 static inline int gcd_i_(int a, int b) { while (b) { int t = a % b; a = b; b = t; } return a; }
 
 int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
-                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                         const float* alpha, const int32_t* tgt_ptr, const int32_t* src, int N, int C, int H, int lmax,
                         int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe, int ldgz, float* da,
                         float* gze_amax, float* g_fc, float* g_Y, cudaStream_t st, bool* handled) {
@@ -761,10 +770,10 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   const size_t smem = R * stage_bytes + tail;
   if (R * stage_bytes + tail > 220 * 1024) return 0;
   if (geo)
-    STAGED_DISPATCH(gata_bwd_tgt_staged_geo_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa,
+    STAGED_DISPATCH(gata_bwd_tgt_staged_geo_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop,
                     alpha, tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y);
   else
-    STAGED_DISPATCH(gata_bwd_tgt_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha,
+    STAGED_DISPATCH(gata_bwd_tgt_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha,
                     tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
@@ -772,7 +781,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
 }
 
 int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, const float* qk, int ldqk, const float* x,
-                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa,
+                        const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                         const float* alpha, const float* da, const int32_t* src_ptr, const int32_t* src_perm,
                         const int32_t* tgt, int N, int C, int H, int lmax, int flags, float* g_qk, int ldgqk, float* g_x,
                         float* g_v, float* g_Xd_in, cudaStream_t st, bool* handled) {
@@ -793,7 +802,7 @@ int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   while (R > 1 && R * stage_bytes + tail > 220 * 1024) --R;
   if (R * stage_bytes + tail > 220 * 1024) return 0;
   const size_t smem = R * stage_bytes + tail;
-  STAGED_DISPATCH(gata_bwd_src_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, alpha,
+  STAGED_DISPATCH(gata_bwd_src_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha,
                   da, src_ptr, src_perm, tgt, N, C, H, R, g_qk, ldgqk, g_x, g_v, g_Xd_in);
   GOTEN_CHECK_LAUNCH();
   *handled = true;

@@ -142,11 +142,19 @@ class GATA(nn.Module):
                 "htr_flags": (1 if self.sep_htr else 0) | (2 if self.update_info["rej"] else 0),
                 "vk_groups": groups}
 
-    def _block(self, plan: GraphPlan, h, Xd, t, Y, fc, kappa, t_amax=None):
+    def _block(self, plan: GraphPlan, h, Xd, t, Y, fc, kappa, t_amax=None, attn_drop_mask=None):
         """h [N,C], Xd [L,N,C], t [E,C] in plan order -> (h', Xd', t', hints); hints = [max|Xd'|, max|t'|] device
         scalars written by the kernels (operand scales of the next GEMMs), t_amax = the same for the input t."""
+        drop = None
         if self.dropout > 0 and self.training:
-            raise NotImplementedError("attention dropout in training mode is not implemented (use attn_dropout=0)")
+            # F.dropout on the scaled attention weights (reference gotennet.py:513): keep mask / (1 - p) per (edge, head),
+            # drawn from torch's CUDA generator (the reference's RNG stream itself is not reproducible across
+            # implementations); the kernels apply it and differentiate through it
+            forced = attn_drop_mask if attn_drop_mask is not None else getattr(self, "_forced_attn_drop", None)
+            drop = forced.to(h.device).float().contiguous() if forced is not None else \
+                (torch.rand(plan.E, self.num_heads, device=h.device) >= self.dropout).float() / (1.0 - self.dropout)
+            if drop.shape != (plan.E, self.num_heads):
+                raise ValueError(f"attention dropout factors must be [E={plan.E}, H={self.num_heads}]")
         Wn1 = torch.cat([self.W_q.weight, self.W_k.weight, self.gamma_s[0].weight, self.gamma_v[0].weight], 0)
         bn1 = torch.cat([self.W_q.bias, self.W_k.bias, self.gamma_s[0].bias, self.gamma_v[0].bias], 0)
         if self.has_htr:
@@ -162,7 +170,7 @@ class GATA(nn.Module):
             Wvq = Wvk = None
         out = ops.GataBlockFn.apply(h, Xd, t, Y, fc, kappa, Wn1, bn1, self.gamma_s[1].weight, self.gamma_s[1].bias,
                                     self.gamma_v[1].weight, self.gamma_v[1].bias, We, be, Wvq, Wvk, plan,
-                                    self._kernel_cfg(), t_amax)
+                                    self._kernel_cfg(), t_amax, drop)
         if self.has_htr:
             return out
         return out[0], out[1], t, out[2]

@@ -366,8 +366,10 @@ class GataBlockFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, plan, cfg, t_amax=None):
-        _chk(h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk)
+    def forward(ctx, h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, plan, cfg, t_amax=None,
+                drop=None):
+        """drop [E,H] (optional): attention dropout factors mask / (1 - p) in plan edge order (gotennet.py:513)."""
+        _chk(h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, drop)
         L_ = lib()
         st = _stream()
         N, C = h.shape
@@ -400,7 +402,7 @@ class GataBlockFn(torch.autograd.Function):
         xd_amax, t1_amax = hints[0:1], hints[1:2]
         am.put(Xd1, xd_amax)
         L_.call("goten_gata_fwd", _ptr(h), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze), ldz, _ptr(Y),
-                _ptr(fc), _ptr(kappa), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax, cfg["gata_flags"],
+                _ptr(fc), _ptr(kappa), _ptr(drop), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax, cfg["gata_flags"],
                 plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), _ptr(xd_amax), st)
         EQK = Wqk = None
         t1 = t
@@ -420,7 +422,9 @@ class GataBlockFn(torch.autograd.Function):
         ctx.plan, ctx.cfg, ctx.htr = plan, cfg, htr
         amx = am.export([h, t, Wn1, Ws2, Wv2, We, Wqk, A1, Xd1 if htr else None])
         ctx.n_amax = len(amx)
-        ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wqk, Z1, A1, x, v, Ze, alpha, Xd1, EQK, *amx)
+        ctx.has_drop = drop is not None
+        ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wqk, Z1, A1, x, v, Ze, alpha, Xd1, EQK, *amx,
+                              *([drop] if drop is not None else []))
         ctx.mark_non_differentiable(hints)
         if htr:
             return h1, Xd1, t1, hints
@@ -436,6 +440,7 @@ class GataBlockFn(torch.autograd.Function):
         plan, cfg, htr = ctx.plan, ctx.cfg, ctx.htr
         am = AmaxScope()
         am.load([h, t, Wn1, Ws2, Wv2, We, Wqk, A1, Xd1 if htr else None], saved[19:19 + ctx.n_amax])
+        drop = saved[19 + ctx.n_amax] if ctx.has_drop else None
         L_ = lib()
         st = _stream()
         N, C = h.shape
@@ -487,14 +492,16 @@ class GataBlockFn(torch.autograd.Function):
         g_Z1 = torch.empty(N, 4 * C, device=dev)
         da = torch.empty(E, H, device=dev)
         L_.call("goten_gata_bwd_tgt", _ptr(g_h1), _ptr(g_Xm), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze),
-                ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(alpha), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax,
+                ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(drop), _ptr(alpha), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H,
+                lmax,
                 cfg["gata_flags"], plan.max_deg_in, _ptr(g_Z1), 4 * C, _ptr(gZe), ldz, _ptr(da), _ptr(g_fc),
                 _ptr(g_Y), _ptr(gze_amax), st)
         g_x = torch.empty(N, SC, device=dev)
         g_v = torch.empty(N, SC, device=dev)
         g_Xd = torch.empty_like(Xd)
         L_.call("goten_gata_bwd_src", _ptr(g_h1), _ptr(g_Xm), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze),
-                ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(alpha), _ptr(da), _ptr(plan.src_ptr), _ptr(plan.src_perm),
+                ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(drop), _ptr(alpha), _ptr(da), _ptr(plan.src_ptr),
+                _ptr(plan.src_perm),
                 _ptr(plan.tgt), N, C, H, lmax, cfg["gata_flags"], _ptr(g_Z1), 4 * C, _ptr(g_x), _ptr(g_v),
                 _ptr(g_Xd), st)
         # gamma_s.1 / gamma_v.1
@@ -525,7 +532,7 @@ class GataBlockFn(torch.autograd.Function):
             dWe.zero_()
             dbe.zero_()
         return (g_h, g_Xd, g_t, g_Y, g_fc, None, dWn1, dbn1, dWs2, dbs2, dWv2, dbv2, dWe, dbe, dWvq, dWvk, None, None,
-                None)
+                None, None)
 
 
 # ---------------------------------------------------------------------------

@@ -180,12 +180,16 @@ int goten_edge_init_bwd(const float* g_t, const float* h, const float* F, int ld
  * L2, segment softmax and scatter-sum done in-CTA (deterministic, no atomics).
  *   qk[N][ldqk]: cols [0,C) = q, [C,2C) = k      x[N][S*C], v[N][S*C]
  *   Xd[L][N][C]   Ze[E][ldz] (see top)           Y[E][L], fc[E], kappa[E]
+ *   drop[E][H] (optional, NULL = none): attention dropout factors mask / (1 - p)
+ *     (gotennet.py:513 F.dropout on the scaled attention weights); alpha[E][H] always
+ *     holds the un-dropped softmax output
  * flags: bit0 = sep_dir, bit1 = sep_tensor.
  * outputs: h_out[N][C] = h + dh, Xd_out = Xd + dX, alpha[E][H] (normalised
  * attention weights, saved for the backward).                                  */
 int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, const float* x,
                    const float* v, const float* Ze, int ldz, const float* Y, const float* fc,
-                   const float* kappa, const int32_t* tgt_ptr, const int32_t* src, int n_nodes,
+                   const float* kappa, const float* drop, const int32_t* tgt_ptr, const int32_t* src,
+                   int n_nodes,
                    int C, int H, int lmax, int flags, int max_deg_in, float* h_out, float* Xd_out,
                    float* alpha, float* xd_amax, void* stream);
 /* backward, target-centric half: needs g_h[N][C], g_Xd[L][N][C] (gradients of the
@@ -196,7 +200,8 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
  * caller zeroes it), consumed by goten_gemm_scaled.                               */
 int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, const float* qk,
                        int ldqk, const float* x, const float* v, const float* Ze, int ldz,
-                       const float* Y, const float* fc, const float* kappa, const float* alpha,
+                       const float* Y, const float* fc, const float* kappa, const float* drop,
+                       const float* alpha,
                        const int32_t* tgt_ptr, const int32_t* src, int n_nodes, int C, int H,
                        int lmax, int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe,
                        int ldgz, float* da, float* g_fc, float* g_Y, float* gze_amax, void* stream);
@@ -204,7 +209,8 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
  * g_Xd_in[L][N][C] = g_Xd + sum over outgoing edges (residual included).      */
 int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, const float* qk,
                        int ldqk, const float* x, const float* v, const float* Ze, int ldz,
-                       const float* Y, const float* fc, const float* kappa, const float* alpha,
+                       const float* Y, const float* fc, const float* kappa, const float* drop,
+                       const float* alpha,
                        const float* da, const int32_t* src_ptr, const int32_t* src_perm,
                        const int32_t* tgt, int n_nodes, int C, int H, int lmax, int flags,
                        float* g_qk, int ldgqk, float* g_x, float* g_v, float* g_Xd_in, void* stream);

@@ -25,6 +25,13 @@ CASES = {
                      atoms=[12, 14], seed=4),
 }
 
+# training-mode attention dropout (configs/model/gotennet.yaml:30 ships attn_dropout 0.1): the generator records the
+# masks the reference's own F.dropout drew (gotennet.py:513) and stores them with the outputs
+DROPOUT_CASES = {
+    "dropout_l2": dict(cfg=OracleConfig(n_atom_basis=64, n_interactions=3, lmax=2, sep_dir=True, sep_tensor=True,
+                                        scale_edge=False), atoms=[15, 3, 19], seed=7, p=0.25),
+}
+
 # read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
 # representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
 HEAD_CASES = {

@@ -298,9 +298,11 @@ def segment_softmax(a: Tensor, index: Tensor, n: int) -> Tensor:
     return e / den[index]
 
 
-def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges):
+def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges, drop=None):
     """GATA.forward / message / aggregate / edge_update (gotennet.py:366-640).
-    h [N,C], X [N,L,C], Y=rl_ij [E,L], t [E,C], r [E], n_edges [E]."""
+    h [N,C], X [N,L,C], Y=rl_ij [E,L], t [E,C], r [E], n_edges [E].
+    drop [E,H] (optional): the realised attention-dropout factors mask / (1 - p) of F.dropout at :513 (training
+    mode); None = eval mode / p = 0."""
     p = f"gata_list.{i}."
     C, H, S, lmax = cfg.n_atom_basis, cfg.num_heads, cfg.S, cfg.lmax
     last = i == cfg.n_interactions - 1
@@ -320,6 +322,8 @@ def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges
         alpha = alpha * (torch.sqrt(n_edges).view(-1, 1) / math.sqrt(C))
     else:
         alpha = alpha * (1.0 / math.sqrt(C))
+    if drop is not None:                                              # :513 F.dropout(attn, p, training)
+        alpha = alpha * drop
     sea = (alpha.unsqueeze(-1) * v[src].view(E, H, S * C // H)).reshape(E, S * C)  # :516-519
     spatial = tf * x[src] * cosine_cutoff(r, cfg.cutoff).unsqueeze(-1)  # :522-526
     o = (spatial + sea).view(E, S, C)                                 # :529-532
@@ -365,7 +369,7 @@ def eqff_layer(sd, cfg: OracleConfig, i: int, h, X):
 
 
 def gotennet_forward(sd, cfg: OracleConfig, z, edge_index, edge_diff, edge_vec,
-                     intermediates: Optional[dict] = None):
+                     intermediates: Optional[dict] = None, drop_masks=None):
     """GotenNet.forward (gotennet.py:956-1010).  Unlike the reference, `edge_vec`
     is NOT mutated in place (quirk App. C.3)."""
     src, tgt = edge_index[0], edge_index[1]
@@ -383,20 +387,21 @@ def gotennet_forward(sd, cfg: OracleConfig, z, edge_index, edge_diff, edge_vec,
     if intermediates is not None:
         intermediates.update(phi=phi, h0=h, t0=t, Y=Y, n_edges=n_edges)
     for i in range(cfg.n_interactions):                                # :995-1007
-        h, X, t = gata_layer(sd, cfg, i, edge_index, h, X, Y, t, edge_diff, n_edges)
+        h, X, t = gata_layer(sd, cfg, i, edge_index, h, X, Y, t, edge_diff, n_edges,
+                             None if drop_masks is None else drop_masks[i])
         h, X = eqff_layer(sd, cfg, i, h, X)
         if intermediates is not None:
             intermediates[f"h{i + 1}"], intermediates[f"X{i + 1}"], intermediates[f"t{i + 1}"] = h, X, t
     return h, X
 
 
-def wrapper_forward(sd, cfg: OracleConfig, z, pos, batch, intermediates: Optional[dict] = None):
-    """GotenNetWrapper.forward (gotennet.py:1043-1045)."""
+def wrapper_forward(sd, cfg: OracleConfig, z, pos, batch, intermediates: Optional[dict] = None, drop_masks=None):
+    """GotenNetWrapper.forward (gotennet.py:1043-1045).  drop_masks: per-layer [E,H] attention-dropout factors."""
     ei = radius_graph(pos.detach(), batch, cfg.cutoff, cfg.max_num_neighbors, loop=True)
     w, vec = edge_geometry(pos, ei)
     if intermediates is not None:
         intermediates.update(edge_index=ei, edge_weight=w, edge_vec=vec)
-    return gotennet_forward(sd, cfg, z, ei, w, vec, intermediates)
+    return gotennet_forward(sd, cfg, z, ei, w, vec, intermediates, drop_masks)
 
 
 # --------------------------------------------------------------------------

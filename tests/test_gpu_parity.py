@@ -41,12 +41,12 @@ class Data:
     pass
 
 
-def build(g, cfg, sd, dev):
+def build(g, cfg, sd, dev, **kw):
     m = g.GotenNetWrapper(n_atom_basis=cfg.n_atom_basis, n_interactions=cfg.n_interactions, n_rbf=cfg.n_rbf,
                           cutoff_fn=g.CosineCutoff(cfg.cutoff), max_z=cfg.max_z, epsilon=cfg.epsilon,
                           num_heads=cfg.num_heads, edge_updates=cfg.edge_updates, scale_edge=cfg.scale_edge,
                           lmax=cfg.lmax, sep_htr=cfg.sep_htr, sep_dir=cfg.sep_dir, sep_tensor=cfg.sep_tensor,
-                          max_num_neighbors=cfg.max_num_neighbors, activation="swish")
+                          max_num_neighbors=cfg.max_num_neighbors, activation="swish", **kw)
     m.load_state_dict(orc.expand_aliases(sd), strict=True)
     return m.to(dev)
 
@@ -196,6 +196,43 @@ def test_golden_forward_backward(g, dev, name, golden_dir):
             assert rel(grad_fingerprint(gr.cpu()), gold[k]) < TOL, k
             n += 1
     assert n == len(orc.state_dict_spec(cfg))
+
+
+def test_attention_dropout_golden(g, dev, golden_dir):
+    """Training-mode attention dropout (reference gotennet.py:513, shipped yaml attn_dropout 0.1): with the masks the
+    reference's own F.dropout drew, forward and every gradient (incl. d/d pos through the force-gradient kernels)
+    match the reference's golden vectors."""
+    from oracle.golden_cases import DROPOUT_CASES
+    for name, spec in DROPOUT_CASES.items():
+        cfg, p = spec["cfg"], spec["p"]
+        gold = np.load(os.path.join(golden_dir, name + ".npz"))
+        z, pos, batch = blob(spec["atoms"], spec["seed"])
+        m = build(g, cfg, orc.make_state_dict(cfg, seed=spec["seed"]), dev, attn_dropout=p)
+        m.train()
+        for gata, mask in zip(m.gata_list, gold["masks"]):
+            gata._forced_attn_drop = torch.from_numpy(mask).float() / (1.0 - p)
+        d = make_data(z, pos, batch, dev)
+        h, X = m(d)
+        assert rel(h.detach(), gold["h"]) < TOL and rel(X.detach(), gold["X"]) < TOL
+        (h.sum() + X.pow(2).sum()).backward()
+        assert rel(d.pos.grad, gold["grad_pos"]) < TOL
+        params = dict(m.named_parameters())
+        for k in gold.files:
+            if k.startswith("grad_") and k != "grad_pos":
+                pr = params[k[5:]]
+                gr = pr.grad if pr.grad is not None else torch.zeros_like(pr)
+                assert rel(grad_fingerprint(gr.cpu()), gold[k]) < TOL, k
+        # eval mode ignores the masks; random masks keep the expectation (E[mask / (1 - p)] = 1)
+        m.eval()
+        h_eval, _ = m(make_data(z, pos, batch, dev, grad=False))
+        assert rel(h_eval.detach(), gold["h"]) > 1e-3
+        m.train()
+        for gata in m.gata_list:
+            gata._forced_attn_drop = None
+        torch.manual_seed(0)
+        hs = torch.stack([m(make_data(z, pos, batch, dev, grad=False))[0].detach() for _ in range(8)])
+        assert (hs[0] - hs[1]).abs().max() > 0                      # fresh masks every call
+        assert rel(hs.mean(0), h_eval.detach().cpu()) < 0.2          # unbiased in expectation (loose: 8 draws)
 
 
 # ------------------------------------- full-width model vs the oracle ----------

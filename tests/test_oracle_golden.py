@@ -138,3 +138,26 @@ def test_oracle_head_modes():
     yn, _ = orc.atomwise_forward(sdh, h, z, batch, 3, "ssp", None)
     assert torch.allclose(ym, ys / torch.tensor([[4.0], [1.0], [6.0]]), atol=1e-6) and torch.equal(yn, yi)
     assert torch.allclose(ys[1], yi[4], atol=1e-6)
+
+
+def test_oracle_dropout_matches_reference_golden(golden_dir):
+    """Training-mode attention dropout (gotennet.py:513): the oracle fed with the masks the reference's own F.dropout
+    drew reproduces the reference's outputs and gradients."""
+    from oracle.golden_cases import DROPOUT_CASES
+    for name, spec in DROPOUT_CASES.items():
+        gold = np.load(os.path.join(golden_dir, name + ".npz"))
+        cfg, p = spec["cfg"], spec["p"]
+        z, pos, batch = blob(spec["atoms"], spec["seed"])
+        sd = {k: v.clone().requires_grad_(v.is_floating_point() and "radial_basis" not in k)
+              for k, v in orc.make_state_dict(cfg, seed=spec["seed"]).items()}
+        drop = [torch.from_numpy(m).float() / (1.0 - p) for m in gold["masks"]]
+        pos_o = pos.clone().requires_grad_(True)
+        h, X = orc.wrapper_forward(sd, cfg, z, pos_o, batch, drop_masks=drop)
+        (h.sum() + X.pow(2).sum()).backward()
+        assert rel(h, torch.from_numpy(gold["h"])) < 1e-6 and rel(X, torch.from_numpy(gold["X"])) < 1e-6
+        assert rel(pos_o.grad, torch.from_numpy(gold["grad_pos"])) < 1e-5
+        for k in gold.files:
+            if k.startswith("grad_") and k != "grad_pos":
+                g = sd[k[5:]].grad
+                g = g if g is not None else torch.zeros_like(sd[k[5:]])
+                assert rel(grad_fingerprint(g), torch.from_numpy(gold[k])) < 1e-4, k
