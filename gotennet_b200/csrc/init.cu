@@ -73,7 +73,7 @@ __global__ void node_init_agg_bwd_src_kernel(const float* __restrict__ g_m, cons
 // ------------------------------------------------------ LayerNorm + SiLU -----
 // one warp per row
 __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, int64_t rows, int C, float eps,
+                                   const float* __restrict__ beta, int64_t rows, int C, float eps, int act,
                                    float* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -89,7 +89,10 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, const float* __r
   }
   const float rs = rsqrtf(warp_sum(v) / (float)C + eps);
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
-  for (int c = lane; c < C; c += 32) y[row * C + c] = siluf_((xr[c] - mu) * rs * gamma[c] + beta[c]);
+  for (int c = lane; c < C; c += 32) {
+    const float zz = (xr[c] - mu) * rs * gamma[c] + beta[c];
+    y[row * C + c] = act ? siluf_(zz) : zz;
+  }
 }
 
 // grid-stride over rows (one warp per row); each warp accumulates d gamma / d beta in its own
@@ -97,7 +100,7 @@ __global__ void ln_silu_fwd_kernel(const float* __restrict__ x, const float* __r
 __global__ void ln_silu_bwd_kernel(const float* __restrict__ g_y, const float* __restrict__ x,
                                    const float* __restrict__ gamma, const float* __restrict__ beta,
                                    const float* __restrict__ mean, const float* __restrict__ rstd, int64_t rows, int C,
-                                   float* __restrict__ g_x, float* __restrict__ g_gamma_part,
+                                   int act, float* __restrict__ g_x, float* __restrict__ g_gamma_part,
                                    float* __restrict__ g_beta_part) {
   extern __shared__ float sm[];  // [nw][2][C]
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -109,7 +112,7 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ g_y, const float* _
     float s1 = 0.f, s2 = 0.f;
     for (int c = lane; c < C; c += 32) {
       const float xh = (x[row * C + c] - mu) * rs;
-      const float dz = g_y[row * C + c] * dsiluf_(xh * gamma[c] + beta[c]);
+      const float dz = act ? g_y[row * C + c] * dsiluf_(xh * gamma[c] + beta[c]) : g_y[row * C + c];
       const float dxh = dz * gamma[c];
       s1 += dxh;
       s2 = fmaf(dxh, xh, s2);
@@ -120,7 +123,7 @@ __global__ void ln_silu_bwd_kernel(const float* __restrict__ g_y, const float* _
     s2 = warp_sum(s2) / (float)C;
     for (int c = lane; c < C; c += 32) {
       const float xh = (x[row * C + c] - mu) * rs;
-      const float dz = g_y[row * C + c] * dsiluf_(xh * gamma[c] + beta[c]);
+      const float dz = act ? g_y[row * C + c] * dsiluf_(xh * gamma[c] + beta[c]) : g_y[row * C + c];
       g_x[row * C + c] = rs * (dz * gamma[c] - s1 - xh * s2);
     }
   }
@@ -242,8 +245,17 @@ int goten_node_init_agg_bwd_src(const float* g_m, const float* F, int ldf, const
 int goten_ln_silu_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int C, float eps, float* y,
                       float* mean, float* rstd, void* stream) {
   if (rows == 0) return 0;
-  ln_silu_fwd_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, as_stream(stream)>>>(x, gamma, beta, rows, C, eps, y, mean,
-                                                                               rstd);
+  ln_silu_fwd_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, as_stream(stream)>>>(x, gamma, beta, rows, C, eps, 1, y,
+                                                                               mean, rstd);
+  GOTEN_CHECK_LAUNCH();
+  return 0;
+}
+
+int goten_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int C, float eps, float* y,
+                        float* mean, float* rstd, void* stream) {
+  if (rows == 0) return 0;
+  ln_silu_fwd_kernel<<<(unsigned)cdiv64(rows, 8), 256, 0, as_stream(stream)>>>(x, gamma, beta, rows, C, eps, 0, y,
+                                                                               mean, rstd);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }
@@ -253,7 +265,17 @@ int goten_ln_silu_bwd(const float* g_y, const float* x, const float* gamma, cons
                       int n_part, void* stream) {
   GOTEN_REQUIRE(n_part >= 1, "n_part must be >= 1");
   ln_silu_bwd_kernel<<<n_part, 256, 8 * 2 * C * sizeof(float), as_stream(stream)>>>(g_y, x, gamma, beta, mean, rstd, rows,
-                                                                                C, g_x, g_gamma_part, g_beta_part);
+                                                                                C, 1, g_x, g_gamma_part, g_beta_part);
+  GOTEN_CHECK_LAUNCH();
+  return 0;
+}
+
+int goten_layernorm_bwd(const float* g_y, const float* x, const float* gamma, const float* beta, const float* mean,
+                        const float* rstd, int64_t rows, int C, float* g_x, float* g_gamma_part, float* g_beta_part,
+                        int n_part, void* stream) {
+  GOTEN_REQUIRE(n_part >= 1, "n_part must be >= 1");
+  ln_silu_bwd_kernel<<<n_part, 256, 8 * 2 * C * sizeof(float), as_stream(stream)>>>(g_y, x, gamma, beta, mean, rstd, rows,
+                                                                                C, 0, g_x, g_gamma_part, g_beta_part);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

@@ -26,7 +26,8 @@ from torch import Tensor, nn
 
 from . import ops
 from .graph import GraphPlan, plan_from_edge_index, radius_graph_plan
-from .layers import (MLP, CosineCutoff, Dense, Distance, EdgeInit, NodeInit, TensorInit, get_weight_init_by_string,
+from .layers import (MLP, CosineCutoff, Dense, Distance, EdgeInit, NodeInit, TensorInit, TensorLayerNorm,
+                     get_weight_init_by_string,
                      is_silu, str2act, str2basis)
 
 
@@ -69,8 +70,8 @@ class GATA(nn.Module):
             raise NotImplementedError(f"edge_updates parts {unsupported} are outside the accelerated path")
         if aggr != "add":
             raise NotImplementedError("only aggr='add' is implemented in the fused message kernel")
-        if layer_norm or steerable_norm or edge_ln:
-            raise NotImplementedError("layer_norm / steerable_norm / edge_ln are outside the accelerated path")
+        if edge_ln:
+            raise NotImplementedError("edge_ln is outside the accelerated path")
         if (evec_dim not in (None, n_atom_basis)) or (emlp_dim not in (None, n_atom_basis)):
             raise NotImplementedError("evec_dim / emlp_dim different from n_atom_basis are not implemented")
         if not is_silu(activation):
@@ -105,8 +106,11 @@ class GATA(nn.Module):
         self.cutoff = CosineCutoff(cutoff)
         self._alpha = None
         self.W_rs = mk(C, C * multiplier, activation=None)
+        # optional pre-norms (reference gotennet.py:306-315): same attribute names / state_dict keys
         self.layernorm_, self.steerable_norm_ = layer_norm, steerable_norm
-        self.layernorm, self.tensor_layernorm = nn.Identity(), nn.Identity()
+        self.layernorm = nn.LayerNorm(n_atom_basis) if layer_norm != "" else nn.Identity()
+        self.tensor_layernorm = (TensorLayerNorm(n_atom_basis, trainable=False, lmax=self.lmax)
+                                 if steerable_norm != "" else nn.Identity())
         self.reset_parameters()
 
     @property
@@ -127,6 +131,10 @@ class GATA(nn.Module):
             self.W_vq.reset_parameters()
             for w in (self.W_vk if self.sep_htr else [self.W_vk]):
                 w.reset_parameters()
+        if self.layernorm_:
+            self.layernorm.reset_parameters()
+        if self.steerable_norm_:
+            self.tensor_layernorm.reset_parameters()
 
     @staticmethod
     def vector_rejection(rep: Tensor, rl_ij: Tensor) -> Tensor:
@@ -155,6 +163,10 @@ class GATA(nn.Module):
                 (torch.rand(plan.E, self.num_heads, device=h.device) >= self.dropout).float() / (1.0 - self.dropout)
             if drop.shape != (plan.E, self.num_heads):
                 raise ValueError(f"attention dropout factors must be [E={plan.E}, H={self.num_heads}]")
+        if self.layernorm_:        # h = self.layernorm(h)            (gotennet.py:397)
+            h = ops.LayerNormFn.apply(h, self.layernorm.weight, self.layernorm.bias, self.layernorm.eps)
+        if self.steerable_norm_:   # X = self.tensor_layernorm(X)     (gotennet.py:398)
+            Xd = ops.TensorLayerNormFn.apply(Xd, self.tensor_layernorm.weight, self.lmax)
         Wn1 = torch.cat([self.W_q.weight, self.W_k.weight, self.gamma_s[0].weight, self.gamma_v[0].weight], 0)
         bn1 = torch.cat([self.W_q.bias, self.W_k.bias, self.gamma_s[0].bias, self.gamma_v[0].bias], 0)
         if self.has_htr:

@@ -248,6 +248,29 @@ class TensorInit(nn.Module):
 
 
 # ------------------------------------------------------------------ init blocks
+class TensorLayerNorm(nn.Module):
+    """Max-min layer normalisation of the steerable features, independently per degree (reference
+    components/layers.py:1497-1563).  forward(X [N,L,C]) -> [N,L,C]; the GATA block calls the kernel directly on the
+    degree-major layout.  `weight` is a buffer unless `trainable` (the reference's GATA uses trainable=False)."""
+
+    def __init__(self, hidden_channels, trainable, lmax=1, **kwargs):
+        super().__init__()
+        if trainable:
+            raise NotImplementedError("TensorLayerNorm(trainable=True) is not used by the reference model and has no "
+                                      "weight gradient here")
+        self.hidden_channels, self.eps, self.lmax = hidden_channels, 1e-12, lmax
+        self.register_buffer("weight", torch.ones(hidden_channels))
+
+    def reset_parameters(self):
+        self.weight.data.fill_(1.0)
+
+    def forward(self, tensor):
+        if tensor.shape[1] != (self.lmax + 1) ** 2 - 1:
+            raise ValueError(f"TensorLayerNorm received unsupported feature dimension {tensor.shape[1]}")
+        Xd = ops.PermuteFn.apply(tensor, True)
+        return ops.PermuteFn.apply(ops.TensorLayerNormFn.apply(Xd, self.weight, self.lmax), False)
+
+
 class NodeInit(nn.Module):
     """Parameters of the node initialisation (reference layers.py:1607-1675):
     A_nbr embedding, W_ndp (rbf -> C), W_nrd_nru (2C -> C -> C with LayerNorm).

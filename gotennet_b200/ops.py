@@ -354,6 +354,71 @@ class InitBlockFn(torch.autograd.Function):
 
 
 # ---------------------------------------------------------------------------
+# optional pre-norms of the GATA block (gotennet.py:306-315, :397-398)
+# ---------------------------------------------------------------------------
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm(C) on h [N,C] (layer_norm != "")."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        _chk(x, gamma, beta)
+        x = _f32(x.contiguous())
+        N, C = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(N, device=x.device)
+        rstd = torch.empty(N, device=x.device)
+        lib().call("goten_layernorm_fwd", _ptr(x), _ptr(gamma), _ptr(beta), N, C, float(eps), _ptr(y), _ptr(mean),
+                   _ptr(rstd), _stream())
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        N, C = x.shape
+        dev = x.device
+        g = g.contiguous()
+        g_x = torch.empty_like(x)
+        n_part = 296
+        gpart = torch.empty(2, n_part, C, device=dev)
+        L_ = lib()
+        st = _stream()
+        L_.call("goten_layernorm_bwd", _ptr(g), _ptr(x), _ptr(gamma), _ptr(beta), _ptr(mean), _ptr(rstd), N, C,
+                _ptr(g_x), _ptr(gpart, 0), _ptr(gpart, n_part * C), n_part, st)
+        dln = torch.empty(2, C, device=dev)
+        ws = workspace(4 * n_part * C * 4, dev)
+        for k in range(2):
+            L_.call("goten_colsum", _ptr(gpart, k * n_part * C), C, n_part, C, _ptr(dln, k * C), _ptr(ws), ws.numel(), st)
+        return g_x, dln[0], dln[1], None
+
+
+class TensorLayerNormFn(torch.autograd.Function):
+    """TensorLayerNorm (layers.py:1497-1563) on degree-major Xd [L,N,C] (steerable_norm != ""); weight is a buffer."""
+
+    @staticmethod
+    def forward(ctx, Xd, weight, lmax):
+        _chk(Xd, weight)
+        Xd = _f32(Xd.contiguous())
+        L, N, C = Xd.shape
+        out = torch.empty_like(Xd)
+        lib().call("goten_tensor_layernorm_fwd", _ptr(Xd), _ptr(weight), N, C, int(lmax), _ptr(out), _stream())
+        ctx.save_for_backward(Xd, weight)
+        ctx.lmax = int(lmax)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        Xd, weight = ctx.saved_tensors
+        L, N, C = Xd.shape
+        g_X = torch.empty_like(Xd)
+        lib().call("goten_tensor_layernorm_bwd", _ptr(g.contiguous()), _ptr(Xd), _ptr(weight), N, C, ctx.lmax, _ptr(g_X),
+                   _stream())
+        return g_X, None, None
+
+
+# ---------------------------------------------------------------------------
 # GATA block: projections + message/softmax/aggregate + HTR edge update
 # ---------------------------------------------------------------------------
 class GataBlockFn(torch.autograd.Function):

@@ -164,6 +164,19 @@ int goten_ln_silu_fwd(const float* x, const float* gamma, const float* beta, int
 int goten_ln_silu_bwd(const float* g_y, const float* x, const float* gamma, const float* beta,
                       const float* mean, const float* rstd, int64_t n_rows, int C, float* g_x,
                       float* g_gamma_part, float* g_beta_part, int n_part, void* stream);
+/* Optional pre-norms of the GATA block (gotennet.py:306-315, :397-398).
+ * goten_layernorm_*: plain nn.LayerNorm (same kernels as above without the SiLU).
+ * goten_tensor_layernorm_*: TensorLayerNorm (layers.py:1497-1563) on Xd[L][N][C]: per degree
+ *   and node, max-min normalisation of the channel norms; weight[C] (buffer, not trained). */
+int goten_layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t n_rows, int C,
+                        float eps, float* y, float* mean, float* rstd, void* stream);
+int goten_layernorm_bwd(const float* g_y, const float* x, const float* gamma, const float* beta,
+                        const float* mean, const float* rstd, int64_t n_rows, int C, float* g_x,
+                        float* g_gamma_part, float* g_beta_part, int n_part, void* stream);
+int goten_tensor_layernorm_fwd(const float* Xd, const float* weight, int n_nodes, int C, int lmax,
+                               float* out, void* stream);
+int goten_tensor_layernorm_bwd(const float* g_out, const float* Xd, const float* weight, int n_nodes,
+                               int C, int lmax, float* g_X, void* stream);
 /* EdgeInit.message (layers.py:1711): t[e][c] = (h[i][c] + h[j][c]) * F[e][C + c]  (self loops kept) */
 int goten_edge_init_fwd(const float* h, const float* F, int ldf, int col0, const int32_t* src,
                         const int32_t* tgt, int64_t n_edges, int C, float* t, float* t_amax,

@@ -32,6 +32,15 @@ DROPOUT_CASES = {
                                         scale_edge=False), atoms=[15, 3, 19], seed=7, p=0.25),
 }
 
+# optional pre-norms of the GATA block: nn.LayerNorm on h + TensorLayerNorm on X
+NORM_CASES = {
+    "norms_l2": dict(cfg=OracleConfig(n_atom_basis=64, n_interactions=3, lmax=2, sep_dir=True, sep_tensor=True,
+                                      scale_edge=False, layernorm="layer", steerable_norm="tensor"),
+                     atoms=[14, 2, 21, 1], seed=8),
+    "norms_l3": dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=3, num_heads=4, scale_edge=True,
+                                      steerable_norm="tensor"), atoms=[11, 9], seed=9),
+}
+
 # read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
 # representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
 HEAD_CASES = {

@@ -54,6 +54,8 @@ class OracleConfig:
     sep_dir: bool = False
     sep_tensor: bool = False
     max_num_neighbors: int = 32
+    layernorm: str = ""        # != "": nn.LayerNorm on h at the top of every GATA block (gotennet.py:308-310, :397)
+    steerable_norm: str = ""   # != "": TensorLayerNorm on X (gotennet.py:311-315, :398)
 
     @property
     def L(self) -> int:
@@ -111,6 +113,11 @@ def state_dict_spec(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]
             sp.append((p + f"{g}.bias", (C,), "bias"))
         sp.append((p + "W_rs.weight", (S * C, C), "weight"))
         sp.append((p + "W_rs.bias", (S * C,), "bias"))
+        if cfg.layernorm:
+            sp.append((p + "layernorm.weight", (C,), "ln_w"))
+            sp.append((p + "layernorm.bias", (C,), "ln_b"))
+        if cfg.steerable_norm:
+            sp.append((p + "tensor_layernorm.weight", (C,), "ln_w"))   # a buffer in the reference (trainable=False)
         if not last and cfg.edge_updates:
             sp.append((p + "gamma_t.dense_layers.0.weight", (C, C), "weight"))
             sp.append((p + "gamma_t.dense_layers.0.bias", (C,), "bias"))
@@ -298,6 +305,24 @@ def segment_softmax(a: Tensor, index: Tensor, n: int) -> Tensor:
     return e / den[index]
 
 
+def tensor_layernorm(X, weight, lmax: int, eps: float = 1e-12):
+    """TensorLayerNorm.forward / max_min_norm (components/layers.py:1523-1563) on X [N,L,C].  The reference's
+    `(dist == 0).all()` early-out returns zeros, which is what the formula below yields for an all-zero part."""
+    parts = []
+    for a0, a1 in degree_slices(lmax):
+        part = X[:, a0:a1]
+        dist = torch.norm(part, dim=1, keepdim=True)                  # :1525
+        dist = dist.clamp(min=eps)                                     # :1530
+        direct = part / dist                                           # :1531
+        max_val, _ = torch.max(dist, dim=-1)                           # :1533
+        min_val, _ = torch.min(dist, dim=-1)
+        delta = (max_val - min_val).view(-1)
+        delta = torch.where(delta == 0, torch.ones_like(delta), delta)  # :1536
+        dist = (dist - min_val.view(-1, 1, 1)) / delta.view(-1, 1, 1)   # :1537
+        parts.append(F.relu(dist) * direct)                            # :1539
+    return torch.cat(parts, dim=1) * weight.unsqueeze(0).unsqueeze(0)  # :1557-1563
+
+
 def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges, drop=None):
     """GATA.forward / message / aggregate / edge_update (gotennet.py:366-640).
     h [N,C], X [N,L,C], Y=rl_ij [E,L], t [E,C], r [E], n_edges [E].
@@ -308,6 +333,10 @@ def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges
     last = i == cfg.n_interactions - 1
     src, tgt = edge_index[0], edge_index[1]
     N, E = h.size(0), t.size(0)
+    if cfg.layernorm:                                                 # :397
+        h = F.layer_norm(h, (C,), sd[p + "layernorm.weight"], sd[p + "layernorm.bias"], 1e-5)
+    if cfg.steerable_norm:                                            # :398
+        X = tensor_layernorm(X, sd[p + "tensor_layernorm.weight"], lmax)
 
     q = _lin(sd, p + "W_q", h).view(N, H, C // H)                     # :400
     k = _lin(sd, p + "W_k", h).view(N, H, C // H)                     # :401

@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import gotennet_oracle as orc  # noqa: E402
-from oracle.golden_cases import CASES, blob as _blob, grad_fingerprint as _gfp  # noqa: E402
+from oracle.golden_cases import CASES, NORM_CASES, blob as _blob, grad_fingerprint as _gfp  # noqa: E402
 from oracle.ref_standins import import_reference  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -41,7 +41,7 @@ def build_reference(ref, cfg: orc.OracleConfig):
         cutoff_fn=CosineCutoff(cfg.cutoff), max_z=cfg.max_z, epsilon=cfg.epsilon, num_heads=cfg.num_heads,
         attn_dropout=0.0, edge_updates=cfg.edge_updates, scale_edge=cfg.scale_edge, lmax=cfg.lmax,
         sep_htr=cfg.sep_htr, sep_dir=cfg.sep_dir, sep_tensor=cfg.sep_tensor,
-        max_num_neighbors=cfg.max_num_neighbors,
+        max_num_neighbors=cfg.max_num_neighbors, layernorm=cfg.layernorm, steerable_norm=cfg.steerable_norm,
     )
 
 
@@ -127,8 +127,10 @@ def run_case(ref, name, spec):
 def main():
     torch.set_num_threads(4)
     ref = import_reference()
-    for name, spec in CASES.items():
-        run_case(ref, name, spec)
+    only = sys.argv[1:]
+    for name, spec in {**CASES, **NORM_CASES}.items():
+        if not only or name in only:
+            run_case(ref, name, spec)
 
 
 if __name__ == "__main__":

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import gotennet_oracle as orc
-from oracle.golden_cases import CASES, blob, grad_fingerprint
+from oracle.golden_cases import CASES, NORM_CASES, blob, grad_fingerprint
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -46,7 +46,8 @@ def build(g, cfg, sd, dev, **kw):
                           cutoff_fn=g.CosineCutoff(cfg.cutoff), max_z=cfg.max_z, epsilon=cfg.epsilon,
                           num_heads=cfg.num_heads, edge_updates=cfg.edge_updates, scale_edge=cfg.scale_edge,
                           lmax=cfg.lmax, sep_htr=cfg.sep_htr, sep_dir=cfg.sep_dir, sep_tensor=cfg.sep_tensor,
-                          max_num_neighbors=cfg.max_num_neighbors, activation="swish", **kw)
+                          max_num_neighbors=cfg.max_num_neighbors, activation="swish", layernorm=cfg.layernorm,
+                          steerable_norm=cfg.steerable_norm, **kw)
     m.load_state_dict(orc.expand_aliases(sd), strict=True)
     return m.to(dev)
 
@@ -170,9 +171,9 @@ def test_gemm_fp16_split_dynamic_range(g, dev):
 
 
 # ------------------------------------------------------- golden vectors -------
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES) + list(NORM_CASES))
 def test_golden_forward_backward(g, dev, name, golden_dir):
-    spec = CASES[name]
+    spec = {**CASES, **NORM_CASES}[name]
     cfg = spec["cfg"]
     gold = np.load(os.path.join(golden_dir, name + ".npz"))
     z, pos, batch = blob(spec["atoms"], spec["seed"])
@@ -195,7 +196,7 @@ def test_golden_forward_backward(g, dev, name, golden_dir):
             gr = p.grad if p.grad is not None else torch.zeros_like(p)
             assert rel(grad_fingerprint(gr.cpu()), gold[k]) < TOL, k
             n += 1
-    assert n == len(orc.state_dict_spec(cfg))
+    assert n == len([k for k, _, _ in orc.state_dict_spec(cfg) if "tensor_layernorm" not in k])  # (a buffer)
 
 
 def test_attention_dropout_golden(g, dev, golden_dir):

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import gotennet_oracle as orc
-from oracle.golden_cases import CASES, blob, grad_fingerprint
+from oracle.golden_cases import CASES, NORM_CASES, blob, grad_fingerprint
 
 TOL = 1e-4  # north_star: within 1e-4 relative, fp32
 
@@ -17,9 +17,9 @@ def rel(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
 
-@pytest.mark.parametrize("name", list(CASES))
+@pytest.mark.parametrize("name", list(CASES) + list(NORM_CASES))
 def test_oracle_matches_reference_golden(name, golden_dir):
-    spec = CASES[name]
+    spec = {**CASES, **NORM_CASES}[name]
     cfg = spec["cfg"]
     gold = np.load(os.path.join(golden_dir, name + ".npz"))
     z, pos, batch = blob(spec["atoms"], spec["seed"])
@@ -45,7 +45,7 @@ def test_oracle_matches_reference_golden(name, golden_dir):
             g = torch.zeros_like(sd[k[5:]]) if g is None else g
             assert rel(grad_fingerprint(g), gold[k]) < TOL, k
             n_checked += 1
-    assert n_checked == len([s for s in orc.state_dict_spec(cfg)])
+    assert n_checked == len([k for k, _, _ in orc.state_dict_spec(cfg) if "tensor_layernorm" not in k])  # (a buffer)
 
 
 def test_fp64_tiebreak(golden_dir):
