@@ -256,7 +256,7 @@ __device__ __forceinline__ void sph_harm(float x, float y, float z, float* Y) {
 template <int LMAX>
 __global__ void edge_geometry_fwd_kernel(const float* __restrict__ pos, const float* __restrict__ vec_in,
                                          const float* __restrict__ r_in, const int32_t* __restrict__ src, const int32_t* __restrict__ tgt,
-                                         const int32_t* __restrict__ deg_out, int64_t E, float rc, int R,
+                                         const int32_t* __restrict__ deg_out, int64_t E, float rc, int R, int basis,
                                          const float* __restrict__ means, const float* __restrict__ betas,
                                          int scale_edge, float inv_sqrt_c, float* __restrict__ r_out,
                                          float* __restrict__ u_out, float* __restrict__ Y_out,
@@ -289,10 +289,20 @@ __global__ void edge_geometry_fwd_kernel(const float* __restrict__ pos, const fl
   const float fc = (r < rc) ? 0.5f * (cosf(r * 3.14159265358979323846f / rc) + 1.0f) : 0.f;
   fc_out[e] = fc;
   kappa_out[e] = scale_edge ? sqrtf((float)deg_out[j]) * inv_sqrt_c : inv_sqrt_c;
-  const float ex = expf((5.0f / rc) * (-r));
-  for (int k = 0; k < R; ++k) {
-    const float d = ex - means[k];
-    phi_out[e * R + k] = fc * expf(-betas[k] * d * d);
+  if (basis == 0) {         // ExpNormalSmearing (layers.py:744-746): cutoff included; means / betas
+    const float ex = expf((5.0f / rc) * (-r));
+    for (int k = 0; k < R; ++k) {
+      const float d = ex - means[k];
+      phi_out[e * R + k] = fc * expf(-betas[k] * d * d);
+    }
+  } else if (basis == 1) {  // BesselBasis (layers.py:349-358): sin(freq r) / r, r = 0 -> divisor 1; means = freqs
+    const float inv = 1.0f / (r == 0.f ? 1.0f : r);
+    for (int k = 0; k < R; ++k) phi_out[e * R + k] = sinf(means[k] * r) * inv;
+  } else {                  // GaussianRBF (layers.py:276-291): means = offsets, betas = widths
+    for (int k = 0; k < R; ++k) {
+      const float d = r - means[k];
+      phi_out[e * R + k] = expf((-0.5f / (betas[k] * betas[k])) * d * d);
+    }
   }
 }
 
@@ -301,7 +311,7 @@ __global__ void edge_geometry_fwd_kernel(const float* __restrict__ pos, const fl
 template <int LMAX>
 __global__ void edge_geometry_bwd_kernel(const float* __restrict__ r_in, const float* __restrict__ u_in,
                                          const int32_t* __restrict__ src, const int32_t* __restrict__ tgt,
-                                         int64_t E, float rc, int R, const float* __restrict__ means,
+                                         int64_t E, float rc, int R, int basis, const float* __restrict__ means,
                                          const float* __restrict__ betas, const float* __restrict__ g_phi,
                                          const float* __restrict__ g_fc, const float* __restrict__ g_Y,
                                          float* __restrict__ g_vec) {
@@ -320,7 +330,7 @@ __global__ void edge_geometry_bwd_kernel(const float* __restrict__ r_in, const f
   const float fc = inside ? 0.5f * (cosf(r * pi_rc) + 1.0f) : 0.f;
   const float dfc = inside ? -0.5f * sinf(r * pi_rc) * pi_rc : 0.f;
   float g_r = g_fc ? g_fc[e] * dfc : 0.f;
-  if (g_phi) {
+  if (g_phi && basis == 0) {
     const float alpha = 5.0f / rc;
     const float ex = expf(-alpha * r);
     for (int k = 0; k < R; ++k) {
@@ -328,6 +338,17 @@ __global__ void edge_geometry_bwd_kernel(const float* __restrict__ r_in, const f
       const float gk = expf(-betas[k] * d * d);
       // phi = fc * gk ; dgk/dr = gk * (-2 beta d) * (-alpha ex)
       g_r += g_phi[e * R + k] * (dfc * gk + fc * gk * (2.0f * betas[k] * d * alpha * ex));
+    }
+  } else if (g_phi && basis == 1) {  // d/dr [sin(a r) / r] = (a r cos(a r) - sin(a r)) / r^2   (r > 0 on non-loop edges)
+    const float inv = 1.0f / r;
+    for (int k = 0; k < R; ++k) {
+      const float ar = means[k] * r;
+      g_r += g_phi[e * R + k] * (ar * cosf(ar) - sinf(ar)) * inv * inv;
+    }
+  } else if (g_phi) {                // d/dr exp(c (r - o)^2) = 2 c (r - o) phi
+    for (int k = 0; k < R; ++k) {
+      const float c = -0.5f / (betas[k] * betas[k]), d = r - means[k];
+      g_r += g_phi[e * R + k] * 2.0f * c * d * expf(c * d * d);
     }
   }
   // ---- angular part: dL/du through the harmonics
@@ -492,7 +513,7 @@ int goten_csr_from_sorted(const int32_t* src, const int32_t* tgt, const int32_t*
 
 int goten_edge_geometry_fwd(const float* pos, const float* edge_vec_in, const float* r_in, const int32_t* src,
                             const int32_t* tgt,
-                            const int32_t* deg_out, int64_t E, int lmax, float cutoff, int n_rbf,
+                            const int32_t* deg_out, int64_t E, int lmax, float cutoff, int n_rbf, int basis,
                             const float* means, const float* betas, int scale_edge, int C, float* r, float* u,
                             float* Y, float* fc, float* kappa, float* phi, void* stream) {
   if (E == 0) return 0;
@@ -502,7 +523,7 @@ int goten_edge_geometry_fwd(const float* pos, const float* edge_vec_in, const fl
   const unsigned nb = (unsigned)cdiv64(E, T);
   const float isc = 1.0f / sqrtf((float)C);
 #define LAUNCH(LM)                                                                                              \
-  edge_geometry_fwd_kernel<LM><<<nb, T, 0, st>>>(pos, edge_vec_in, r_in, src, tgt, deg_out, E, cutoff, n_rbf, means,   \
+  edge_geometry_fwd_kernel<LM><<<nb, T, 0, st>>>(pos, edge_vec_in, r_in, src, tgt, deg_out, E, cutoff, n_rbf, basis, means,   \
                                                 betas, scale_edge, isc, r, u, Y, fc, kappa, phi)
   if (lmax == 1) LAUNCH(1); else if (lmax == 2) LAUNCH(2); else LAUNCH(3);
 #undef LAUNCH
@@ -511,7 +532,7 @@ int goten_edge_geometry_fwd(const float* pos, const float* edge_vec_in, const fl
 }
 
 int goten_edge_geometry_bwd(const float* r, const float* u, const int32_t* src, const int32_t* tgt, int64_t E,
-                            int lmax, float cutoff, int n_rbf, const float* means, const float* betas,
+                            int lmax, float cutoff, int n_rbf, int basis, const float* means, const float* betas,
                             const float* g_phi, const float* g_fc, const float* g_Y, float* g_vec, void* stream) {
   if (E == 0) return 0;
   GOTEN_REQUIRE(lmax >= 1 && lmax <= 3, "lmax=%d unsupported (1..3)", lmax);
@@ -519,7 +540,7 @@ int goten_edge_geometry_bwd(const float* r, const float* u, const int32_t* src, 
   const int T = 128;
   const unsigned nb = (unsigned)cdiv64(E, T);
 #define LAUNCH(LM)                                                                                        \
-  edge_geometry_bwd_kernel<LM><<<nb, T, 0, st>>>(r, u, src, tgt, E, cutoff, n_rbf, means, betas, g_phi,    \
+  edge_geometry_bwd_kernel<LM><<<nb, T, 0, st>>>(r, u, src, tgt, E, cutoff, n_rbf, basis, means, betas, g_phi,    \
                                                 g_fc, g_Y, g_vec)
   if (lmax == 1) LAUNCH(1); else if (lmax == 2) LAUNCH(2); else LAUNCH(3);
 #undef LAUNCH

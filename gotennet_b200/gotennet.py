@@ -271,8 +271,9 @@ class GotenNet(nn.Module):
         self.edge_init = EdgeInit(n_rbf, n_atom_basis)
         basis_cls = str2basis(radial_basis)
         self.radial_basis = basis_cls(cutoff=self.cutoff, n_rbf=n_rbf)
-        if type(self.radial_basis).__name__ != "ExpNormalSmearing" or getattr(self.radial_basis, "trainable", False):
-            raise NotImplementedError("the fused geometry kernel implements the non-trainable expnorm basis only")
+        if not hasattr(self.radial_basis, "kernel_args") or getattr(self.radial_basis, "trainable", False):
+            raise NotImplementedError("the fused geometry kernel implements the non-trainable expnorm, BesselBasis and "
+                                      "GaussianRBF bases")
         self.A_na = nn.Embedding(max_z, n_atom_basis, padding_idx=0)
         self.sphere = TensorInit(l=lmax)
         self.gata_list = nn.ModuleList([
@@ -321,9 +322,9 @@ class GotenNet(nn.Module):
 
     # -- fused core -----------------------------------------------------------
     def _geometry(self, plan: GraphPlan, pos=None, edge_vec=None, edge_diff=None):
-        rb = self.radial_basis
-        return ops.EdgeGeometryFn.apply(pos, edge_vec, edge_diff, rb.means, rb.betas, plan, self.sphere.l,
-                                        self.cutoff, self.scale_edge, self.n_atom_basis)
+        basis, p0, p1 = self.radial_basis.kernel_args()
+        return ops.EdgeGeometryFn.apply(pos, edge_vec, edge_diff, p0.float().contiguous(), p1.float().contiguous(), plan,
+                                        self.sphere.l, self.cutoff, self.scale_edge, self.n_atom_basis, basis)
 
     def _core(self, z: Tensor, plan: GraphPlan, Y, fc, kappa, phi) -> Tuple[Tensor, Tensor]:
         C, L = self.n_atom_basis, self.sphere.tensor_size

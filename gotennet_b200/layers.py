@@ -206,15 +206,60 @@ class ExpNormalSmearing(nn.Module):
         d = dist.unsqueeze(-1)
         return self.cutoff_fn(d) * torch.exp(-self.betas * (torch.exp(self.alpha * (-d)) - self.means) ** 2)
 
+    def kernel_args(self):
+        """(basis id, p0, p1) for goten_edge_geometry_*."""
+        return 0, self.means, self.betas
+
+
+class GaussianRBF(nn.Module):
+    """Gaussian radial basis (reference layers.py:276-325): exp(-0.5 (d - offset_k)^2 / width_k^2); no cutoff factor."""
+
+    def __init__(self, n_rbf: int, cutoff: float, start: float = 0.0, trainable: bool = False):
+        super().__init__()
+        if trainable:
+            raise NotImplementedError("the fused geometry kernel has no gradient for trainable basis parameters")
+        self.n_rbf = n_rbf
+        offset = torch.linspace(start, cutoff, n_rbf)
+        self.register_buffer("widths", torch.abs(offset[1] - offset[0]) * torch.ones_like(offset))
+        self.register_buffer("offsets", offset)
+
+    def forward(self, inputs):
+        coeff = -0.5 / torch.pow(self.widths, 2)
+        return torch.exp(coeff * torch.pow(inputs[..., None] - self.offsets, 2))
+
+    def kernel_args(self):
+        return 2, self.offsets, self.widths
+
+
+class BesselBasis(nn.Module):
+    """0th-order Bessel radial basis sin(k pi d / r_c) / d (reference layers.py:328-358); d = 0 divides by 1."""
+
+    def __init__(self, cutoff=5.0, n_rbf=None, trainable=False):
+        super().__init__()
+        if n_rbf is None:
+            raise ValueError("n_rbf must be specified for BesselBasis")
+        self.n_rbf = n_rbf
+        self.register_buffer("freqs", torch.arange(1, n_rbf + 1) * math.pi / cutoff)
+        self.register_buffer("norm1", torch.tensor(1.0))
+
+    def forward(self, inputs):
+        x = inputs[..., None]
+        return torch.sin(x * self.freqs[None, :]) / torch.where(x == 0, self.norm1, x)
+
+    def kernel_args(self):
+        return 1, self.freqs, self.freqs
+
 
 def str2basis(name):
-    """reference layers.py:749-777; only the basis the fused geometry kernel implements."""
+    """reference layers.py:749-777 (same quirk: 'GaussianRBF' is matched case-sensitively)."""
     if not isinstance(name, str):
         return name
+    if _norm_name(name) == "besselbasis":
+        return BesselBasis
+    if name == "GaussianRBF":
+        return GaussianRBF
     if name.lower() == "expnorm":
         return ExpNormalSmearing
-    if _norm_name(name) in ("besselbasis", "gaussianrbf"):
-        raise NotImplementedError(f"radial basis {name!r} is outside the accelerated path (expnorm only)")
     raise ValueError("Unknown radial basis: {}".format(name))
 
 

@@ -228,7 +228,7 @@ class EdgeGeometryFn(torch.autograd.Function):
     components/layers.py:1591-1604, :744-746, :149-152, :805-869; gotennet.py:978-989."""
 
     @staticmethod
-    def forward(ctx, pos, edge_vec, r_in, means, betas, plan, lmax, cutoff, scale_edge, C):
+    def forward(ctx, pos, edge_vec, r_in, means, betas, plan, lmax, cutoff, scale_edge, C, basis=0):
         E, L, R = plan.E, (lmax + 1) ** 2 - 1, means.numel()
         dev = plan.src.device
         _chk(pos, edge_vec, r_in, means, betas)
@@ -239,9 +239,9 @@ class EdgeGeometryFn(torch.autograd.Function):
         kappa = torch.empty(E, device=dev)
         phi = torch.empty(E, R, device=dev)
         lib().call("goten_edge_geometry_fwd", _ptr(pos), _ptr(edge_vec), _ptr(r_in), _ptr(plan.src), _ptr(plan.tgt),
-                   _ptr(plan.deg_out), E, lmax, float(cutoff), R, _ptr(means), _ptr(betas), int(scale_edge), C,
+                   _ptr(plan.deg_out), E, lmax, float(cutoff), R, int(basis), _ptr(means), _ptr(betas), int(scale_edge), C,
                    _ptr(r), _ptr(u), _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(phi), _stream())
-        ctx.plan, ctx.lmax, ctx.cutoff = plan, lmax, float(cutoff)
+        ctx.plan, ctx.lmax, ctx.cutoff, ctx.basis = plan, lmax, float(cutoff), int(basis)
         ctx.from_pos = pos is not None
         ctx.n_pos = pos.shape[0] if pos is not None else 0
         ctx.save_for_backward(r, u, means, betas)
@@ -259,7 +259,7 @@ class EdgeGeometryFn(torch.autograd.Function):
         g_fc = g_fc.contiguous() if g_fc is not None else None
         g_phi = g_phi.contiguous() if g_phi is not None else None
         lib().call("goten_edge_geometry_bwd", _ptr(r), _ptr(u), _ptr(plan.src), _ptr(plan.tgt), E, ctx.lmax,
-                   ctx.cutoff, means.numel(), _ptr(means), _ptr(betas), _ptr(g_phi), _ptr(g_fc), _ptr(g_Y),
+                   ctx.cutoff, means.numel(), ctx.basis, _ptr(means), _ptr(betas), _ptr(g_phi), _ptr(g_fc), _ptr(g_Y),
                    _ptr(g_vec), _stream())
         if g_r is not None:
             g_vec = g_vec + g_r.unsqueeze(-1) * u  # d|v|/dv = u (self loops: u = 0)
@@ -267,8 +267,8 @@ class EdgeGeometryFn(torch.autograd.Function):
             g_pos = torch.empty(ctx.n_pos, 3, device=r.device)
             lib().call("goten_edge_vec_to_pos_bwd", _ptr(g_vec), _ptr(plan.tgt_ptr), _ptr(plan.src_ptr),
                        _ptr(plan.src_perm), ctx.n_pos, _ptr(g_pos), _stream())
-            return g_pos, None, None, None, None, None, None, None, None, None
-        return None, g_vec, None, None, None, None, None, None, None, None
+            return g_pos, None, None, None, None, None, None, None, None, None, None
+        return None, g_vec, None, None, None, None, None, None, None, None, None
 
 
 # ---------------------------------------------------------------------------

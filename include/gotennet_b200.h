@@ -81,17 +81,20 @@ int goten_csr_from_sorted(const int32_t* src, const int32_t* tgt, const int32_t*
  *      phi[E][n_rbf]
  * If `edge_vec_in` != NULL the vectors are taken from it ([E][3], un-normalised,
  * GotenNet.forward's argument) instead of pos[src]-pos[tgt]; if `r_in` != NULL the
- * distances fed to the radial basis / cutoff are taken from it (edge_diff).     */
+ * distances fed to the radial basis / cutoff are taken from it (edge_diff).
+ * basis (layers.py:749-777): 0 = expnorm (means, betas; cosine cutoff folded in, :744-746),
+ *   1 = BesselBasis sin(f r) / r (means = freqs; :349-358), 2 = GaussianRBF (means = offsets,
+ *   betas = widths; :276-291).                                                     */
 int goten_edge_geometry_fwd(const float* pos, const float* edge_vec_in, const float* r_in, const int32_t* src,
                             const int32_t* tgt, const int32_t* deg_out, int64_t n_edges, int lmax,
-                            float cutoff, int n_rbf, const float* means, const float* betas,
+                            float cutoff, int n_rbf, int basis, const float* means, const float* betas,
                             int scale_edge, int n_atom_basis, float* r, float* u, float* Y,
                             float* fc, float* kappa, float* phi, void* stream);
 /* d(loss)/d(edge_vec) from the gradients of phi, fc and Y (first-order forces,
  * outputs.py:365-375 needs d/dpos).  g_vec[E][3]; the caller scatters it to pos. */
 int goten_edge_geometry_bwd(const float* r, const float* u, const int32_t* src, const int32_t* tgt,
-                            int64_t n_edges, int lmax, float cutoff, int n_rbf, const float* means,
-                            const float* betas, const float* g_phi, const float* g_fc,
+                            int64_t n_edges, int lmax, float cutoff, int n_rbf, int basis,
+                            const float* means, const float* betas, const float* g_phi, const float* g_fc,
                             const float* g_Y, float* g_vec, void* stream);
 /* scatter of per-edge vector gradients onto positions: g_pos[i] = sum_{e: src=i} g - sum_{e: tgt=i} g */
 int goten_edge_vec_to_pos_bwd(const float* g_vec, const int32_t* tgt_ptr, const int32_t* src_ptr,

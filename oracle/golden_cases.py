@@ -41,6 +41,15 @@ NORM_CASES = {
                                       steerable_norm="tensor"), atoms=[11, 9], seed=9),
 }
 
+# the other registered radial bases (layers.py:749-777); merged into NORM_CASES' test parametrisation
+NORM_CASES.update({
+    "bessel_l1": dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=1, num_heads=4, n_rbf=20,
+                                       radial_basis="BesselBasis"), atoms=[13, 6], seed=10),
+    "gauss_l2": dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, num_heads=4, n_rbf=24, sep_dir=True,
+                                      sep_tensor=True, scale_edge=False, radial_basis="GaussianRBF"),
+                     atoms=[10, 12], seed=11),
+})
+
 # read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
 # representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
 HEAD_CASES = {

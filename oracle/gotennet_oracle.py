@@ -54,6 +54,7 @@ class OracleConfig:
     sep_dir: bool = False
     sep_tensor: bool = False
     max_num_neighbors: int = 32
+    radial_basis: str = "expnorm"   # "expnorm" | "BesselBasis" | "GaussianRBF" (layers.py:749-777)
     layernorm: str = ""        # != "": nn.LayerNorm on h at the top of every GATA block (gotennet.py:308-310, :397)
     steerable_norm: str = ""   # != "": TensorLayerNorm on X (gotennet.py:311-315, :398)
 
@@ -170,7 +171,17 @@ def make_state_dict(cfg: OracleConfig, seed: int = 0, bias_scale: float = 0.1,
                 t[0].zero_()
         sd[key] = t.to(dtype)
     means, betas = rbf_buffers(cfg, dtype)
-    sd["radial_basis.means"], sd["radial_basis.betas"] = means, betas
+    if cfg.radial_basis == "expnorm":
+        sd["radial_basis.means"], sd["radial_basis.betas"] = means, betas
+    elif cfg.radial_basis == "BesselBasis":                        # layers.py:345-347
+        sd["radial_basis.freqs"] = (torch.arange(1, cfg.n_rbf + 1) * math.pi / cfg.cutoff).to(dtype)
+        sd["radial_basis.norm1"] = torch.tensor(1.0, dtype=dtype)
+    elif cfg.radial_basis == "GaussianRBF":                        # layers.py:313-316
+        offset = torch.linspace(0.0, cfg.cutoff, cfg.n_rbf)
+        sd["radial_basis.widths"] = (torch.abs(offset[1] - offset[0]) * torch.ones_like(offset)).to(dtype)
+        sd["radial_basis.offsets"] = offset.to(dtype)
+    else:
+        raise ValueError(cfg.radial_basis)
     return sd
 
 
@@ -239,6 +250,18 @@ def expnorm_rbf(d: Tensor, means: Tensor, betas: Tensor, rc: float) -> Tensor:
     d = d.unsqueeze(-1)
     alpha = 5.0 / rc
     return cosine_cutoff(d, rc) * torch.exp(-betas * (torch.exp(alpha * (-d)) - means) ** 2)
+
+
+def radial_basis(sd, cfg: OracleConfig, d: Tensor) -> Tensor:
+    """self.radial_basis(edge_diff) (gotennet.py:974) for the three registered bases (layers.py:749-777)."""
+    if cfg.radial_basis == "expnorm":
+        return expnorm_rbf(d, sd["radial_basis.means"], sd["radial_basis.betas"], cfg.cutoff)
+    x = d.unsqueeze(-1)
+    if cfg.radial_basis == "BesselBasis":                          # layers.py:349-358
+        norm = torch.where(x == 0, sd["radial_basis.norm1"], x)
+        return torch.sin(x * sd["radial_basis.freqs"][None, :]) / norm
+    coeff = -0.5 / torch.pow(sd["radial_basis.widths"], 2)         # layers.py:288-291
+    return torch.exp(coeff * torch.pow(x - sd["radial_basis.offsets"], 2))
 
 
 def sph_harm(lmax: int, u: Tensor) -> Tensor:
@@ -403,7 +426,7 @@ def gotennet_forward(sd, cfg: OracleConfig, z, edge_index, edge_diff, edge_vec,
     is NOT mutated in place (quirk App. C.3)."""
     src, tgt = edge_index[0], edge_index[1]
     h = sd["A_na.weight"][z]                                           # :973
-    phi = expnorm_rbf(edge_diff, sd["radial_basis.means"], sd["radial_basis.betas"], cfg.cutoff)  # :974
+    phi = radial_basis(sd, cfg, edge_diff)                              # :974
     h = node_init(sd, cfg, z, h, edge_index, edge_diff, phi)           # :976
     t = edge_init(sd, edge_index, phi, h)                              # :977
     mask = (src != tgt).unsqueeze(-1)                                  # :978-980

@@ -67,10 +67,14 @@ def test_constructor_errors(g):
         g.GATA(64, torch.nn.functional.silu, edge_updates="bogus")  # gotennet.py:164-167
     with pytest.raises(NotImplementedError):
         g.GATA(64, torch.nn.functional.silu, edge_updates="gated")
-    with pytest.raises(NotImplementedError):
-        g.GotenNet(cutoff_fn=g.CosineCutoff(5.0), radial_basis="BesselBasis")
+    m = g.GotenNet(n_atom_basis=32, n_interactions=1, cutoff_fn=g.CosineCutoff(5.0), radial_basis="BesselBasis", n_rbf=8)
+    assert set(k for k in m.state_dict() if k.startswith("radial_basis.")) == {"radial_basis.freqs", "radial_basis.norm1"}
+    m = g.GotenNet(n_atom_basis=32, n_interactions=1, cutoff_fn=g.CosineCutoff(5.0), radial_basis="GaussianRBF", n_rbf=8)
+    assert set(k for k in m.state_dict() if k.startswith("radial_basis.")) == {"radial_basis.widths", "radial_basis.offsets"}
     with pytest.raises(ValueError):
         g.GotenNet(cutoff_fn=g.CosineCutoff(5.0), radial_basis="nope")
+    with pytest.raises(ValueError):
+        g.GotenNet(cutoff_fn=g.CosineCutoff(5.0), radial_basis="gaussianrbf")  # the reference matches this name case-sensitively
     with pytest.raises(ValueError):
         g.GotenNet(cutoff_fn=g.CosineCutoff(5.0), activation="nope")
 
