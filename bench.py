@@ -311,7 +311,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(budget_s=20.0)
-        print(json.dumps(out), flush=True)
+        print(json.dumps(out), file=_RESULT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -376,10 +376,25 @@ def run_reference(args):
                                f"(PyTorch restatement of the reference) on {cores} host threads, {n_mol}-molecule sample per step"},
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }), file=_RESULT, flush=True)
+
+
+_RESULT = sys.stdout
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to fd 1
+    when NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the whole run and the result line goes to a
+    private duplicate of the original stdout."""
+    global _RESULT
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    _RESULT = os.fdopen(real, "w")
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
