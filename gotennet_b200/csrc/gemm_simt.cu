@@ -367,13 +367,16 @@ int goten_gemm_scaled(const float* A, int lda, int trans_a, const float* B, int 
   cudaStream_t st = as_stream(stream);
   static int auto16 = -1;
   if (auto16 < 0) { const char* e = getenv("GOTEN_TC16"); auto16 = e ? atoi(e) : 1; }
+  // negative impl = "prefer arm |impl|, fall back to the fp32 SIMT arm for shapes it declines" (GOTEN_GEMM=tc|tc16)
+  const bool strict = impl > 0;
+  if (impl < 0) impl = -impl;
   if (impl == 3 || (impl == 0 && auto16)) {
     bool handled = false;
     int rc = gemm_tc16(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, add_src, ld_add, act_out, ld_act,
                        act_lo, act_hi, colsum, a_amax, b_amax, workspace, workspace_bytes, st, &handled);
     if (rc) return rc;
     if (handled) return 0;
-    GOTEN_REQUIRE(impl == 0, "tcgen05 fp16 GEMM does not support this shape/layout (M=%d N=%d K=%d ta=%d tb=%d)", M, N,
+    GOTEN_REQUIRE(!strict, "tcgen05 fp16 GEMM does not support this shape/layout (M=%d N=%d K=%d ta=%d tb=%d)", M, N,
                   K, trans_a, trans_b);
   }
   if (impl == 0 || impl == 2) {
@@ -382,7 +385,7 @@ int goten_gemm_scaled(const float* A, int lda, int trans_a, const float* B, int 
                      act_hi, colsum, workspace, workspace_bytes, st, &handled);
     if (rc) return rc;
     if (handled) return 0;
-    GOTEN_REQUIRE(impl == 0, "tcgen05 GEMM does not support this shape/layout (M=%d N=%d K=%d ta=%d tb=%d)", M, N, K,
+    GOTEN_REQUIRE(!strict, "tcgen05 GEMM does not support this shape/layout (M=%d N=%d K=%d ta=%d tb=%d)", M, N, K,
                   trans_a, trans_b);
   }
   return gemm_simt(A, lda, trans_a, B, ldb, trans_b, C, ldc, M, N, K, bias, add_src, ld_add, act_out, ld_act, act_lo,

@@ -22,7 +22,9 @@ import torch
 from ._lib import GotenError, lib
 
 _WS = {}
-_IMPL = {"simt": 1, "tc": 2, "tc16": 3, "auto": 0}
+# GOTEN_GEMM: auto = split-fp16 -> 3xTF32 -> SIMT (first arm that accepts the shape); tc / tc16 = prefer that tensor-core
+# arm and fall back to SIMT (negative impl code); simt = exact-fp32 SIMT only.  Explicit positive codes are strict.
+_IMPL = {"simt": 1, "tc": -2, "tc16": -3, "auto": 0}
 
 
 def gemm_impl() -> int:
@@ -101,7 +103,7 @@ class AmaxScope:
     uses them (operand scaling), so the scope is inert under GOTEN_GEMM=simt|tc or GOTEN_TC16=0."""
 
     def __init__(self):
-        self.enabled = gemm_impl() in (0, 3) and os.environ.get("GOTEN_TC16", "1") != "0"
+        self.enabled = gemm_impl() in (0, -3) and os.environ.get("GOTEN_TC16", "1") != "0"
         self._d = {}
         self._pool, self._used = None, 0
 

@@ -116,6 +116,7 @@ int goten_edge_vec_to_pos_bwd(const float* g_vec, const int32_t* tgt_ptr, const 
  *     fused into the weight-gradient GEMM).
  * `workspace` (split-K partials): at least goten_gemm_workspace_bytes(...) bytes.
  * impl: 0 = auto (first arm that accepts the shape, in the order 3, 2, 1), 1 = fp32 SIMT,
+ *       (a negative code -2 / -3 prefers that arm and falls back to 1 instead of failing)
  *       2 = tcgen05 3xTF32, 3 = tcgen05 split-fp16 (x*2^s = hi + lo in fp16, three
  *       kind::f16 MMAs, fp32 accumulation; 22 significant bits).
  * goten_gemm_scaled: same, with optional DEVICE pointers to an upper bound of max|A| /
