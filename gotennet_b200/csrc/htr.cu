@@ -78,42 +78,36 @@ __device__ __forceinline__ void htr_grad(const float* k, const float* y, const f
   if (LMAX >= 3) group_grad<8, 15>(k, y, n[2], dw, out);
 }
 
-// weight and gradient w.r.t. q in one pass (target half of the backward): returns the group's weight
-template <int LO, int HI>
-__device__ __forceinline__ float group_weight_grad(const float* q, const float* k, const float* y, float n, float dw,
-                                                   float* out) {
+// weight and gradient w.r.t. q in one pass (target half of the backward): returns the group's weight.
+// GY: also the gradient w.r.t. the harmonics (forces), from the same dot products:
+//   d/dy_m [q.k - n (q.y)(k.y)] = -n (b q_m + a k_m) + 2 a b y_m        (a = q.y, b = k.y, dn/dy_m = -2 y_m)
+template <int LO, int HI, bool GY>
+__device__ __forceinline__ float group_weight_grad(const float* q, const float* k, const float* y, float n, bool rej,
+                                                   float dw, float* out, float* gy) {
   float a = 0.f, b = 0.f, s = 0.f;
 #pragma unroll
   for (int m = LO; m < HI; ++m) { a = fmaf(q[m], y[m], a); b = fmaf(k[m], y[m], b); s = fmaf(q[m], k[m], s); }
   const float nb = n * b, cy = -dw * nb;
 #pragma unroll
   for (int m = LO; m < HI; ++m) out[m] = fmaf(dw, k[m], fmaf(cy, y[m], out[m]));
+  if (GY) {
+    const float ca = -dw * n * a, cab = rej ? 2.0f * dw * a * b : 0.f;  // rejection off: n is the constant 0
+#pragma unroll
+    for (int m = LO; m < HI; ++m) gy[m] += fmaf(cy, q[m], fmaf(ca, k[m], cab * y[m]));
+  }
   return fmaf(-nb, a, s);
 }
 
-template <int LMAX>
+template <int LMAX, bool GY>
 __device__ __forceinline__ float htr_weight_grad(const float* q, const float* k, const float* y, const float* n, int flags,
-                                                 float dw, float* out) {
+                                                 float dw, float* out, float* gy) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
-  if (!(flags & HTR_SEP)) return group_weight_grad<0, L>(q, k, y, n[0], dw, out);
-  float w = group_weight_grad<0, 3>(q, k, y, n[0], dw, out);
-  if (LMAX >= 2) w += group_weight_grad<3, 8>(q, k, y, n[1], dw, out);
-  if (LMAX >= 3) w += group_weight_grad<8, 15>(q, k, y, n[2], dw, out);
+  const bool rej = flags & HTR_REJ;
+  if (!(flags & HTR_SEP)) return group_weight_grad<0, L, GY>(q, k, y, n[0], rej, dw, out, gy);
+  float w = group_weight_grad<0, 3, GY>(q, k, y, n[0], rej, dw, out, gy);
+  if (LMAX >= 2) w += group_weight_grad<3, 8, GY>(q, k, y, n[1], rej, dw, out, gy);
+  if (LMAX >= 3) w += group_weight_grad<8, 15, GY>(q, k, y, n[2], rej, dw, out, gy);
   return w;
-}
-
-// d w / d y_m for one group (rejection on): w = sum (q - a y)(k - b y), a = q.y, b = k.y
-template <int LO, int HI>
-__device__ __forceinline__ void group_grad_y(const float* q, const float* k, const float* y, float dw, float* gy) {
-  float a = 0.f, b = 0.f;
-#pragma unroll
-  for (int m = LO; m < HI; ++m) { a = fmaf(q[m], y[m], a); b = fmaf(k[m], y[m], b); }
-  float sq = 0.f, sk = 0.f;  // sum y (q - a y), sum y (k - b y)
-#pragma unroll
-  for (int m = LO; m < HI; ++m) { sq = fmaf(y[m], q[m] - a * y[m], sq); sk = fmaf(y[m], k[m] - b * y[m], sk); }
-#pragma unroll
-  for (int m = LO; m < HI; ++m)
-    gy[m] = dw * (-a * (k[m] - b * y[m]) - b * (q[m] - a * y[m]) - sk * q[m] - sq * k[m]);
 }
 
 // ---- V-wide channel vectors (V = 4: 128-bit loads/stores; V = 1 fallback)
@@ -266,24 +260,11 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
           col_of<L, V>(gq, qq, gc);
           const float sg = sigmoid_fast_(zt[qq]);
           const float dw = dt[qq] * zt[qq] * sg;                 // dt * silu(zt)
-          const float w = htr_weight_grad<LMAX>(qc, kc, y, nn, flags, dw, gc);
+          const float w = htr_weight_grad<LMAX, GY>(qc, kc, y, nn, flags, dw, gc, gy);
           gz[qq] = dt[qq] * w * sg * (1.0f + zt[qq] * (1.0f - sg));  // dt * w * silu'(zt)
           amx = fmaxf(amx, fabsf(gz[qq]));
 #pragma unroll
           for (int m = 0; m < L; ++m) gq[m][qq] = gc[m];
-          if (GY && (flags & HTR_REJ)) {
-            float g1[L];
-#pragma unroll
-            for (int m = 0; m < L; ++m) g1[m] = 0.f;
-            if (!(flags & HTR_SEP)) group_grad_y<0, L>(qc, kc, y, dw, g1);
-            else {
-              group_grad_y<0, 3>(qc, kc, y, dw, g1);
-              if (LMAX >= 2) group_grad_y<3, 8>(qc, kc, y, dw, g1);
-              if (LMAX >= 3) group_grad_y<8, 15>(qc, kc, y, dw, g1);
-            }
-#pragma unroll
-            for (int m = 0; m < L; ++m) gy[m] += g1[m];
-          }
         }
         stv<V>(gZe + (size_t)e * ldgz + zt_col0 + c, gz);
       }

@@ -50,6 +50,11 @@ NORM_CASES.update({
                      atoms=[10, 12], seed=11),
 })
 
+# edge_updates="norej": HTR without the vector rejection (gotennet.py:176-177, :583-599)
+NORM_CASES["norej_l2"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, num_heads=4, sep_dir=True,
+                                               sep_tensor=True, scale_edge=False, edge_updates="norej"),
+                              atoms=[12, 8], seed=12)
+
 # read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
 # representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
 HEAD_CASES = {

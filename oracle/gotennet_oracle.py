@@ -401,10 +401,13 @@ def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges
             groups = [(0, cfg.L)]
         EQi, EKj = EQ[tgt], EK[src]                                    # _i = target, _j = source
         w = 0
-        for a0, a1 in groups:                                          # :580-609 (rejection on, :351-364)
+        rej = not (isinstance(cfg.edge_updates, str) and "norej" in cfg.edge_updates.split("_"))   # :176-177
+        for a0, a1 in groups:                                          # :580-609 (rejection :351-364)
             y = Y[:, a0:a1, None]
-            Qr = EQi[:, a0:a1] - (EQi[:, a0:a1] * y).sum(1, keepdim=True) * y
-            Kr = EKj[:, a0:a1] - (EKj[:, a0:a1] * y).sum(1, keepdim=True) * y
+            Qr, Kr = EQi[:, a0:a1], EKj[:, a0:a1]
+            if rej:
+                Qr = Qr - (Qr * y).sum(1, keepdim=True) * y
+                Kr = Kr - (Kr * y).sum(1, keepdim=True) * y
             w = w + (Qr * Kr).sum(1)
         t = t + F.silu(_lin(sd, p + "gamma_t.dense_layers.0", t)) * w  # :611, :445
     return h, X, t
