@@ -14,6 +14,21 @@
 namespace goten {
 
 constexpr int HTR_SEP = 1, HTR_REJ = 2;
+// bits 2-3 of `flags`: gamma_w of the "gated" / "gatedt" / "act" edge-update variants (gotennet.py:283-289):
+// 0 = identity (default), 1 = sigmoid, 2 = tanh, 3 = SiLU applied to the scalar weight w before it multiplies gamma_t(t)
+__device__ __forceinline__ int htr_gate(int flags) { return (flags >> 2) & 3; }
+__device__ __forceinline__ float gate_f(float w, int gate) {
+  if (gate == 1) return sigmoidf_(w);
+  if (gate == 2) return tanhf(w);
+  if (gate == 3) return siluf_(w);
+  return w;
+}
+__device__ __forceinline__ float gate_df(float w, int gate) {
+  if (gate == 1) { const float s = sigmoidf_(w); return s * (1.0f - s); }
+  if (gate == 2) { const float t = tanhf(w); return 1.0f - t * t; }
+  if (gate == 3) return dsiluf_(w);
+  return 1.0f;
+}
 
 // Rejection algebra.  With P = I - y y^T applied per group (degree l if sep_htr, else all of L):
 //   (P q).(P k) = q.k - (q.y)(k.y) n,      n = 2 - |y|^2     (n = 0 switches the rejection off)
@@ -186,6 +201,7 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   const int i = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
+  const int gate = htr_gate(flags);
   float amx = 0.f;
   float q[L][V];
 #pragma unroll
@@ -204,7 +220,7 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
       float qc[L], kc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(k, qq, kc);
-      tv[qq] = fmaf(siluf_(zt[qq]), htr_weight<LMAX>(qc, kc, y, nn, flags), tv[qq]);
+      tv[qq] = fmaf(siluf_(zt[qq]), gate_f(htr_weight<LMAX>(qc, kc, y, nn, flags), gate), tv[qq]);
       amx = fmaxf(amx, fabsf(tv[qq]));
     }
     stv<V>(t_out + (size_t)e * C + c, tv);
@@ -227,6 +243,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
   __shared__ float gy_scratch[GY ? 2 * L * (GY_MAX_BLOCK + 4) : 1];
   const int i = blockIdx.x, c = threadIdx.x * V;
   const bool act = c < C;
+  const int gate = htr_gate(flags);
   float amx = 0.f;
   float q[L][V], gq[L][V];
 #pragma unroll
@@ -259,9 +276,10 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
           col_of<L, V>(k, qq, kc);
           col_of<L, V>(gq, qq, gc);
           const float sg = sigmoid_fast_(zt[qq]);
-          const float dw = dt[qq] * zt[qq] * sg;                 // dt * silu(zt)
+          float dw = dt[qq] * zt[qq] * sg;                       // dt * silu(zt)
+          if (gate) dw *= gate_df(htr_weight<LMAX>(qc, kc, y, nn, flags), gate);   // ... * gamma_w'(w)
           const float w = htr_weight_grad<LMAX, GY>(qc, kc, y, nn, flags, dw, gc, gy);
-          gz[qq] = dt[qq] * w * sg * (1.0f + zt[qq] * (1.0f - sg));  // dt * w * silu'(zt)
+          gz[qq] = dt[qq] * gate_f(w, gate) * sg * (1.0f + zt[qq] * (1.0f - sg));  // dt * gamma_w(w) * silu'(zt)
           amx = fmaxf(amx, fabsf(gz[qq]));
 #pragma unroll
           for (int m = 0; m < L; ++m) gq[m][qq] = gc[m];
@@ -322,11 +340,14 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   const int j = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
-  float gk[L][V];
+  const int gate = htr_gate(flags);
+  float gk[L][V], kown[L][V];   // kown: this node's EK rows, needed only to re-evaluate w for a gated gamma_w
 #pragma unroll
-  for (int m = 0; m < L; ++m)
+  for (int m = 0; m < L; ++m) {
 #pragma unroll
-    for (int qq = 0; qq < V; ++qq) gk[m][qq] = 0.f;
+    for (int qq = 0; qq < V; ++qq) { gk[m][qq] = 0.f; kown[m][qq] = 0.f; }
+    if (gate) ldv<V>(EK + ((size_t)m * N + j) * ldp + c, kown[m]);
+  }
   for (int p = src_ptr[j]; p < src_ptr[j + 1]; ++p) {
     const int e = src_perm[p];
     const int i = tgt[e];
@@ -342,7 +363,13 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
       float qc[L], gc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(gk, qq, gc);
-      htr_grad<LMAX>(qc, y, nn, flags, dt[qq] * silu_fast_(zt[qq]), gc);  // d w / d k: q <-> k symmetric
+      float dw = dt[qq] * silu_fast_(zt[qq]);
+      if (gate) {
+        float kc[L];
+        col_of<L, V>(kown, qq, kc);
+        dw *= gate_df(htr_weight<LMAX>(qc, kc, y, nn, flags), gate);
+      }
+      htr_grad<LMAX>(qc, y, nn, flags, dw, gc);  // d w / d k: q <-> k symmetric
 #pragma unroll
       for (int m = 0; m < L; ++m) gk[m][qq] = gc[m];
     }

@@ -65,7 +65,7 @@ class GATA(nn.Module):
         parts = edge_updates.split("_") if isinstance(edge_updates, str) and edge_updates else []
         if not all(p in _ALLOWED_UPDATE_PARTS for p in parts):
             raise ValueError(f"Invalid edge update parts. Allowed parts are {_ALLOWED_UPDATE_PARTS}")
-        unsupported = [p for p in parts if p != "norej"]
+        unsupported = [p for p in parts if p not in ("norej", "gated", "gatedt", "act")]
         if unsupported:
             raise NotImplementedError(f"edge_updates parts {unsupported} are outside the accelerated path")
         if aggr != "add":
@@ -78,7 +78,11 @@ class GATA(nn.Module):
             raise NotImplementedError("the fused kernels implement SiLU ('swish') only")
         if not 1 <= lmax <= 3:
             raise NotImplementedError("lmax must be 1..3")
-        self.update_info = {"gated": False, "rej": "norej" not in parts, "mlp": False, "mlpa": False, "lin_w": 0,
+        gated = False  # reference gotennet.py:168-173: later parts override earlier ones
+        for name in ("gated", "gatedt", "act"):
+            if name in parts:
+                gated = name
+        self.update_info = {"gated": gated, "rej": "norej" not in parts, "mlp": False, "mlpa": False, "lin_w": 0,
                             "lin_ln": 0}
         self.sep_htr, self.sep_dir, self.sep_tensor = sep_htr, sep_dir, sep_tensor
         self.epsilon, self.last_layer, self.edge_updates, self.scale_edge = epsilon, last_layer, edge_updates, scale_edge
@@ -102,7 +106,9 @@ class GATA(nn.Module):
                 self.W_vk = nn.ModuleList([mk(C, C, activation=None, bias=False) for _ in range(lmax)])
             else:
                 self.W_vk = mk(C, C, activation=None, bias=False)
-            self.gamma_w = nn.Sequential()
+            # gamma_w (reference :270-292): an optional gate on the scalar HTR weight; evaluated inside the HTR kernels
+            gate_mod = {"gated": nn.Sigmoid, "gatedt": nn.Tanh, "act": nn.SiLU}.get(gated)
+            self.gamma_w = nn.Sequential(*([gate_mod()] if gate_mod else []))
         self.cutoff = CosineCutoff(cutoff)
         self._alpha = None
         self.W_rs = mk(C, C * multiplier, activation=None)
@@ -147,7 +153,8 @@ class GATA(nn.Module):
         groups = _degree_ranges(self.lmax) if self.sep_htr else [(0, (self.lmax + 1) ** 2 - 1)]
         return {"H": self.num_heads, "lmax": self.lmax, "S": self.multiplier,
                 "gata_flags": (1 if self.sep_dir else 0) | (2 if self.sep_tensor else 0),
-                "htr_flags": (1 if self.sep_htr else 0) | (2 if self.update_info["rej"] else 0),
+                "htr_flags": (1 if self.sep_htr else 0) | (2 if self.update_info["rej"] else 0) |
+                             ({False: 0, "gated": 1, "gatedt": 2, "act": 3}[self.update_info["gated"]] << 2),
                 "vk_groups": groups}
 
     def _block(self, plan: GraphPlan, h, Xd, t, Y, fc, kappa, t_amax=None, attn_drop_mask=None):

@@ -238,7 +238,9 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
  *   w[e][c] = sum_l sum_m rej(EQ_i)^l_m rej(EK_j)^l_m ;  t_out = t + silu(zt) * w
  * zt = Ze[:, zt_col0 : zt_col0+C).  EQ / EK / g_EQ / g_EK rows have pitch ldp floats
  * (ldp = 2C with EK = EQ + C when both projections come from one GEMM with the stacked
- * weight [W_vq; W_vk]).  flags: bit0 = sep_htr (rejection per degree),
+ * weight [W_vq; W_vk]).  flags bits 2-3: gamma_w of the gated edge updates (0 identity,
+ * 1 sigmoid "gated", 2 tanh "gatedt", 3 SiLU "act"; gotennet.py:283-289).
+ * flags: bit0 = sep_htr (rejection per degree),
  * bit1 = rejection enabled.                                                    */
 int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
                   int zt_col0, const float* t, const int32_t* tgt_ptr, const int32_t* src,

@@ -55,6 +55,12 @@ NORM_CASES["norej_l2"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2
                                                sep_tensor=True, scale_edge=False, edge_updates="norej"),
                               atoms=[12, 8], seed=12)
 
+# gated edge updates: gamma_w = Sigmoid ("gated"), Tanh ("gatedt"), SiLU ("act") on the scalar HTR weight (:283-289)
+for _i, _flag in enumerate(["gated", "gatedt_norej", "act"]):
+    NORM_CASES["eu_" + _flag] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2 if _i != 1 else 1,
+                                                      num_heads=4, sep_dir=True, sep_tensor=True, scale_edge=bool(_i % 2),
+                                                      edge_updates=_flag), atoms=[11, 7], seed=13 + _i)
+
 # read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
 # representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
 HEAD_CASES = {

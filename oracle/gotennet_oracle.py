@@ -409,6 +409,13 @@ def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges
                 Qr = Qr - (Qr * y).sum(1, keepdim=True) * y
                 Kr = Kr - (Kr * y).sum(1, keepdim=True) * y
             w = w + (Qr * Kr).sum(1)
+        parts = cfg.edge_updates.split("_") if isinstance(cfg.edge_updates, str) else []
+        if "act" in parts:                                             # gamma_w, :283-289 (later parts win, :168-173)
+            w = F.silu(w)
+        elif "gatedt" in parts:
+            w = torch.tanh(w)
+        elif "gated" in parts:
+            w = torch.sigmoid(w)
         t = t + F.silu(_lin(sd, p + "gamma_t.dense_layers.0", t)) * w  # :611, :445
     return h, X, t
 
