@@ -193,7 +193,8 @@ __device__ __forceinline__ void fill_meta(EdgeMeta<(LMAX + 1) * (LMAX + 1) - 1>&
   __syncthreads();
 }
 
-template <int LMAX, int V>
+// GATED: a gamma_w gate is configured (flags bits 2-3); the plain instantiation folds it away
+template <int LMAX, int V, bool GATED>
 __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                const float* __restrict__ Ze, int ldz, int zt_col0, const float* __restrict__ t,
                                const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
@@ -201,7 +202,7 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   const int i = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
-  const int gate = htr_gate(flags);
+  const int gate = GATED ? htr_gate(flags) : 0;
   float amx = 0.f;
   float q[L][V];
 #pragma unroll
@@ -229,7 +230,7 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
 }
 
 // GY: also produce the geometry gradient g_Y (forces); kept out of the common instantiation (registers)
-template <int LMAX, int V, bool GY>
+template <int LMAX, int V, bool GY, bool GATED>
 __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
                                                  const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                                  const float* __restrict__ Ze, int ldz, int zt_col0,
@@ -243,7 +244,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
   __shared__ float gy_scratch[GY ? 2 * L * (GY_MAX_BLOCK + 4) : 1];
   const int i = blockIdx.x, c = threadIdx.x * V;
   const bool act = c < C;
-  const int gate = htr_gate(flags);
+  const int gate = GATED ? htr_gate(flags) : 0;
   float amx = 0.f;
   float q[L][V], gq[L][V];
 #pragma unroll
@@ -307,7 +308,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
   }
 }
 
-template <int LMAX, int V>
+template <int LMAX, int V, bool GATED>
 __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
                                    const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
@@ -315,10 +316,10 @@ __global__ void htr_bwd_tgt_kernel(const float* __restrict__ g_t_out, const floa
                                    int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
                                    float* __restrict__ g_Y, float* __restrict__ gze_amax,
                                    float* __restrict__ geq_amax) {
-  htr_bwd_tgt_body<LMAX, V, false>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
+  htr_bwd_tgt_body<LMAX, V, false, GATED>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
                                    gze_amax, geq_amax);
 }
-template <int LMAX, int V>
+template <int LMAX, int V, bool GATED>
 __global__ void htr_bwd_tgt_gy_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
                                       const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                       const float* __restrict__ Ze, int ldz, int zt_col0,
@@ -326,11 +327,11 @@ __global__ void htr_bwd_tgt_gy_kernel(const float* __restrict__ g_t_out, const f
                                       int C, int flags, float* __restrict__ g_EQ, float* __restrict__ gZe, int ldgz,
                                       float* __restrict__ g_Y, float* __restrict__ gze_amax,
                                       float* __restrict__ geq_amax) {
-  htr_bwd_tgt_body<LMAX, V, true>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
+  htr_bwd_tgt_body<LMAX, V, true, GATED>(g_t_out, EQ, EK, ldp, Y, Ze, ldz, zt_col0, tgt_ptr, src, N, C, flags, g_EQ, gZe, ldgz, g_Y,
                                   gze_amax, geq_amax);
 }
 
-template <int LMAX, int V>
+template <int LMAX, int V, bool GATED>
 __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const float* __restrict__ EQ,
                                    const float* __restrict__ EK, int ldp, const float* __restrict__ Y,
                                    const float* __restrict__ Ze, int ldz, int zt_col0,
@@ -340,7 +341,7 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   const int j = blockIdx.x, c = threadIdx.x * V;
   if (c >= C) return;
-  const int gate = htr_gate(flags);
+  const int gate = GATED ? htr_gate(flags) : 0;
   float gk[L][V], kown[L][V];   // kown: this node's EK rows, needed only to re-evaluate w for a gated gamma_w
 #pragma unroll
   for (int m = 0; m < L; ++m) {
@@ -399,29 +400,35 @@ static inline int htr_vec(int def) {
 
 using namespace goten;
 
-#define HTR_DISPATCH(KERNEL, V4OK, VDEF, ...)                                                      \
+#define HTR_LAUNCH(KERNEL, LM, VV, T, ...)                                                      \
+  do {                                                                                         \
+    if ((flags >> 2) & 3) KERNEL<LM, VV, true><<<N, T, 0, st>>>(__VA_ARGS__);                  \
+    else KERNEL<LM, VV, false><<<N, T, 0, st>>>(__VA_ARGS__);                                  \
+  } while (0)
+
+#define HTR_DISPATCH(KERNEL, V4OK, VDEF, ...)                                                  \
   do {                                                                                         \
     GOTEN_REQUIRE(lmax >= 1 && lmax <= 3, "lmax=%d unsupported (1..3)", lmax);                 \
     GOTEN_REQUIRE(C >= 1 && C <= 4096, "n_atom_basis=%d unsupported (<=4096)", C);             \
     if (N == 0) return 0;                                                                      \
     cudaStream_t st = as_stream(stream);                                                       \
-    if ((V4OK) && htr_vec(VDEF) == 2) {                                                          \
+    if ((V4OK) && htr_vec(VDEF) == 2) {                                                        \
       const int T = block_for(C, 2);                                                           \
       GOTEN_REQUIRE(T <= 1024, "n_atom_basis=%d too wide for the 2-channel HTR kernels", C);   \
-      if (lmax == 1) KERNEL<1, 2><<<N, T, 0, st>>>(__VA_ARGS__);                               \
-      else if (lmax == 2) KERNEL<2, 2><<<N, T, 0, st>>>(__VA_ARGS__);                          \
-      else KERNEL<3, 2><<<N, T, 0, st>>>(__VA_ARGS__);                                         \
+      if (lmax == 1) HTR_LAUNCH(KERNEL, 1, 2, T, __VA_ARGS__);                                 \
+      else if (lmax == 2) HTR_LAUNCH(KERNEL, 2, 2, T, __VA_ARGS__);                            \
+      else HTR_LAUNCH(KERNEL, 3, 2, T, __VA_ARGS__);                                           \
     } else if (V4OK) {                                                                         \
       const int T = block_for(C, 4);                                                           \
-      if (lmax == 1) KERNEL<1, 4><<<N, T, 0, st>>>(__VA_ARGS__);                               \
-      else if (lmax == 2) KERNEL<2, 4><<<N, T, 0, st>>>(__VA_ARGS__);                          \
-      else KERNEL<3, 4><<<N, T, 0, st>>>(__VA_ARGS__);                                         \
+      if (lmax == 1) HTR_LAUNCH(KERNEL, 1, 4, T, __VA_ARGS__);                                 \
+      else if (lmax == 2) HTR_LAUNCH(KERNEL, 2, 4, T, __VA_ARGS__);                            \
+      else HTR_LAUNCH(KERNEL, 3, 4, T, __VA_ARGS__);                                           \
     } else {                                                                                   \
       const int T = block_for(C, 1);                                                           \
       GOTEN_REQUIRE(T <= 1024, "n_atom_basis=%d needs 16-byte aligned rows", C);               \
-      if (lmax == 1) KERNEL<1, 1><<<N, T, 0, st>>>(__VA_ARGS__);                               \
-      else if (lmax == 2) KERNEL<2, 1><<<N, T, 0, st>>>(__VA_ARGS__);                          \
-      else KERNEL<3, 1><<<N, T, 0, st>>>(__VA_ARGS__);                                         \
+      if (lmax == 1) HTR_LAUNCH(KERNEL, 1, 1, T, __VA_ARGS__);                                 \
+      else if (lmax == 2) HTR_LAUNCH(KERNEL, 2, 1, T, __VA_ARGS__);                            \
+      else HTR_LAUNCH(KERNEL, 3, 1, T, __VA_ARGS__);                                           \
     }                                                                                          \
     GOTEN_CHECK_LAUNCH();                                                                      \
     return 0;                                                                                  \
