@@ -321,123 +321,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else {
-    // =============================== epilogue ===================================
-    const int q = warp & 3;
-    uint8_t* my_buf = epi_smem + (warp - EPI_WARP0) * 2 * 4096;
-    const bool fast = (p.add_src == nullptr) && (p.act_out == nullptr);
-    const float un_a = inv_scale_of(*p.amax_a), un_b = inv_scale_of(*p.amax_b);
-    uint32_t tile_it = 0, n_store = 0;
-    for (int w = unit; w < n_items; w += n_units, ++tile_it) {
-      const int split = w / n_tiles, tile = w % n_tiles;
-      const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN;
-      const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
-      mbar_wait(bar_tfull + 8 * acc, aph);
-      tc_fence_after();
-      const int row_base = m0 + q * 32;
-      const bool rows_live = row_base < p.M;
-      for (int ch = 0; ch < BN / 32; ++ch) {
-        const int nc0 = n0 + ch * 32;
-        if (nc0 >= p.N) break;
-        const uint32_t taddr = tmem_base + acc * (uint32_t)BN + ch * 32 + ((uint32_t)(q * 32) << 16);
-        uint32_t r[32];
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!rows_live) continue;
-        float bl = 0.f;
-        if (p.bias && !p.partial && nc0 + lane < p.N) bl = p.bias[nc0 + lane];
-        uint8_t* buf = my_buf + (n_store & 1) * 4096;
-        if (fast && n_store >= 2) {
-          if (lane == 0) bulk_wait_read<1>();
-          __syncwarp();
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          float4 v;
-          v.x = __uint_as_float(r[4 * c + 0]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 0);
-          v.y = __uint_as_float(r[4 * c + 1]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 1);
-          v.z = __uint_as_float(r[4 * c + 2]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 2);
-          v.w = __uint_as_float(r[4 * c + 3]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 3);
-          *reinterpret_cast<float4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
-        }
-        if (fast) {
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (p.partial) tma_store_2d(&tmC, smem_u32(buf), nc0, split * p.M + row_base);
-            else tma_store_2d(&tmC, smem_u32(buf), nc0, row_base);
-            bulk_commit();
-          }
-          ++n_store;
-        } else {
-          __syncwarp();
-          const int cq = lane & 7, rsub = lane >> 3;
-          const int n = nc0 + cq * 4;
-          const bool vec_ok = (n + 3 < p.N);
-          float4 addv[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub, m = row_base + rr;
-            addv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.add_src && m < p.M) {
-              const float* ap = p.add_src + (size_t)m * p.ld_add + n;
-              if (vec_ok && p.add_vec) addv[i] = *reinterpret_cast<const float4*>(ap);
-              else {
-                if (n + 0 < p.N) addv[i].x = ap[0];
-                if (n + 1 < p.N) addv[i].y = ap[1];
-                if (n + 2 < p.N) addv[i].z = ap[2];
-                if (n + 3 < p.N) addv[i].w = ap[3];
-              }
-            }
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub, m = row_base + rr;
-            float4 v = *reinterpret_cast<const float4*>(buf + rr * 128 + ((cq ^ (rr & 7)) << 4));
-            v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
-            if (m < p.M) {
-              float* cp = p.C + (size_t)m * p.ldc + n;
-              if (vec_ok && p.c_vec) *reinterpret_cast<float4*>(cp) = v;
-              else {
-                if (n + 0 < p.N) cp[0] = v.x;
-                if (n + 1 < p.N) cp[1] = v.y;
-                if (n + 2 < p.N) cp[2] = v.z;
-                if (n + 3 < p.N) cp[3] = v.w;
-              }
-              if (p.act_out && p.act_vec && n >= p.act_lo && n + 3 < p.act_hi) {  // whole float4 inside the SiLU range
-                float4 a;
-                a.x = __fdividef(v.x, 1.0f + __expf(-v.x)); a.y = __fdividef(v.y, 1.0f + __expf(-v.y));
-                a.z = __fdividef(v.z, 1.0f + __expf(-v.z)); a.w = __fdividef(v.w, 1.0f + __expf(-v.w));
-                *reinterpret_cast<float4*>(p.act_out + (size_t)m * p.ld_act + (n - p.act_lo)) = a;
-              } else if (p.act_out) {
-                const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                for (int qd = 0; qd < 4; ++qd) {
-                  const int nn = n + qd;
-                  if (nn < p.N && nn >= p.act_lo && nn < p.act_hi)
-                    p.act_out[(size_t)m * p.ld_act + (nn - p.act_lo)] = vv[qd] / (1.0f + __expf(-vv[qd]));
-                }
-              }
-            }
-          }
-          __syncwarp();
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        if (NCTA == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
-        else mbar_arrive(bar_tempty + 8 * acc);
-      }
-    }
-    if (fast && lane == 0) bulk_wait_all();
+    // =============================== epilogue (umma.cuh) ========================
+    gemm_epilogue<NCTA, BM, EPI_WARP0>(p, tmC, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
+                                       n_tiles, BN, rank, inv_scale_of(*p.amax_a), inv_scale_of(*p.amax_b));
   }
 
   tc_fence_before();
