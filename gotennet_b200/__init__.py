@@ -15,3 +15,4 @@ from .outputs import Atomwise, ScaleShift, SchnetMLP, shifted_softplus  # noqa: 
 from .optim import FusedAdamW  # noqa: F401
 from .parallel import FlatGradBuffer, shard_bounds, take_shard  # noqa: F401
 from .data import MoleculeBatch, collate  # noqa: F401
+from .training import energy_and_forces, force_matching_backward  # noqa: F401

@@ -498,3 +498,55 @@ def test_training_steps_with_fused_optimizer(g, dev):
     assert losses[-1] < 0.7 * losses[0], losses
     lo, hi = opt.flat_p.data_ptr(), opt.flat_p.data_ptr() + 4 * opt.flat_p.numel()
     assert all(lo <= p.data_ptr() < hi for p in params)
+
+
+# ------------------------------------------- force-matching training step -----
+@pytest.mark.gpu
+def test_force_matching_step_vs_oracle(g, dev):
+    """force_matching_backward (central-difference mixed derivative, first-order kernels only) against the oracle's
+    EXACT double backward through the forces (create_graph=True, outputs.py:371) in float64: energy / forces to the
+    usual bar, the parameter gradient of an energy + force loss to 5e-3 of its largest entry (documented
+    approximation, gotennet_b200/training.py)."""
+    cfg = orc.OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, num_heads=4, sep_dir=True, sep_tensor=True,
+                           scale_edge=False)
+    z, pos, batch = blob([9, 12, 5], 21)
+    n_mol = 3
+    sd = orc.make_state_dict(cfg, seed=21)
+    sdh = orc.make_head_state_dict(cfg.n_atom_basis, seed=21)
+    gen = torch.Generator().manual_seed(5)
+    E_t = torch.randn(n_mol, 1, generator=gen)
+    F_t = torch.randn(z.numel(), 3, generator=gen) * 0.5
+
+    def loss_fn(E, F):
+        return (E - E_t.to(E)).pow(2).mean() + 10.0 * (F - F_t.to(F)).pow(2).mean()
+
+    # oracle, float64, exact second order
+    sd64 = {k: v.double().requires_grad_(v.is_floating_point() and "radial_basis" not in k) for k, v in sd.items()}
+    sdh64 = {k: v.double().requires_grad_(k.startswith("out_net")) for k, v in sdh.items()}
+    Eo, Fo, _ = orc.energy_and_forces(sd64, sdh64, cfg, z, pos.double(), batch, n_mol, "silu")
+    Lo = loss_fn(Eo, Fo)
+    Lo.backward()
+
+    rep = build(g, cfg, sd, dev)
+    head = build_head(g, cfg, sdh, "silu", dev)
+    d = DataNS()
+    d.z, d.pos, d.batch, d.num_graphs = z.to(dev), pos.to(dev), batch.to(dev), n_mol
+    E1, F1 = g.energy_and_forces(rep, head, d)
+    assert rel(E1, Eo.detach()) < TOL and rel(F1, Fo.detach()) < TOL
+    loss, E, F = g.force_matching_backward(rep, head, d, loss_fn)
+    assert abs(float(loss) - float(Lo.detach())) < 1e-4 * abs(float(Lo.detach()))
+    rp, hp = dict(rep.named_parameters()), dict(head.named_parameters())
+    worst = 0.0
+    for k, v in sd64.items():
+        if v.grad is not None and k in rp:
+            worst = max(worst, rel(rp[k].grad, v.grad))
+    for k, v in sdh64.items():
+        if v.grad is not None and k in hp:
+            worst = max(worst, rel(hp[k].grad, v.grad))
+    assert worst < 5e-3, worst
+    # the force term matters: an energy-only gradient is far off
+    for p in list(rp.values()) + list(hp.values()):
+        p.grad = None
+    g.force_matching_backward(rep, head, d, lambda E_, F_: (E_ - E_t.to(E_)).pow(2).mean())
+    far = max(rel(rp[k].grad, v.grad) for k, v in sd64.items() if v.grad is not None and k in rp)
+    assert far > 0.05
