@@ -1,5 +1,5 @@
 """GPU: the data-gradient GEMM with the fused residual add (EQFF / HTR backward shape), for ncu source captures.
-Exploration tool, not collected by pytest.   python tests/gpu_gemm_add.py [with_add=1]"""
+Exploration tool, not collected by pytest.   python tools/gpu_gemm_add.py [with_add=1]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,5 +1,5 @@
 """GPU: one pass of the three GEMM forms at the cfg2 edge shape, for `ncu --metrics gpu__time_duration.sum`
-(exploration tool, not collected by pytest).   python tests/gpu_gemm_big.py [impl] [M N K]"""
+(exploration tool, not collected by pytest).   python tools/gpu_gemm_big.py [impl] [M N K]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -1,6 +1,6 @@
 """GPU: accuracy and speed of the tensor-core GEMM arms (2 = tcgen05 3xTF32, 3 = tcgen05 split-fp16) vs the
 fp32 SIMT arm (1), all through goten_gemm_scaled.  Exploration tool, not collected by pytest.
-    python tests/gpu_gemm_check.py [quick] [impls=1,2,3] [scale=1e-6]"""
+    python tools/gpu_gemm_check.py [quick] [impls=1,2,3] [scale=1e-6]"""
 import os
 import sys
 

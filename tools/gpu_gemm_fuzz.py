@@ -1,5 +1,5 @@
 """GPU: random-shape check of the split-fp16 GEMM arm (all three forms, fused epilogues, tails) against fp64.
-Exploration tool, not collected by pytest.   python tests/gpu_gemm_fuzz.py [n_shapes] [seed]"""
+Exploration tool, not collected by pytest.   python tools/gpu_gemm_fuzz.py [n_shapes] [seed]"""
 import os, sys, random
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

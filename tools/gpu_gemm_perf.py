@@ -1,5 +1,5 @@
 """GPU: accuracy (vs fp64) and timing of goten_gemm at the shapes of the cfg2 step (exploration tool,
-not collected by pytest).   python tests/gpu_gemm_perf.py [quick]"""
+not collected by pytest).   python tools/gpu_gemm_perf.py [quick]"""
 import os, sys
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
