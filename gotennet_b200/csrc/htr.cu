@@ -17,6 +17,8 @@ constexpr int HTR_SEP = 1, HTR_REJ = 2;
 // bits 2-3 of `flags`: gamma_w of the "gated" / "gatedt" / "act" edge-update variants (gotennet.py:283-289):
 // 0 = identity (default), 1 = sigmoid, 2 = tanh, 3 = SiLU applied to the scalar weight w before it multiplies gamma_t(t)
 __device__ __forceinline__ int htr_gate(int flags) { return (flags >> 2) & 3; }
+// bit 4: gamma_t ends without an activation ("mlp" variant, gotennet.py:244-248): zt is used as is instead of SiLU(zt)
+constexpr int HTR_T_LINEAR = 16;
 __device__ __forceinline__ float gate_f(float w, int gate) {
   if (gate == 1) return sigmoidf_(w);
   if (gate == 2) return tanhf(w);
@@ -221,7 +223,8 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
       float qc[L], kc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(k, qq, kc);
-      tv[qq] = fmaf(siluf_(zt[qq]), gate_f(htr_weight<LMAX>(qc, kc, y, nn, flags), gate), tv[qq]);
+      const float gt_ = (GATED && (flags & HTR_T_LINEAR)) ? zt[qq] : siluf_(zt[qq]);
+      tv[qq] = fmaf(gt_, gate_f(htr_weight<LMAX>(qc, kc, y, nn, flags), gate), tv[qq]);
       amx = fmaxf(amx, fabsf(tv[qq]));
     }
     stv<V>(t_out + (size_t)e * C + c, tv);
@@ -276,11 +279,13 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
           col_of<L, V>(q, qq, qc);
           col_of<L, V>(k, qq, kc);
           col_of<L, V>(gq, qq, gc);
+          const bool t_lin = GATED && (flags & HTR_T_LINEAR);
           const float sg = sigmoid_fast_(zt[qq]);
-          float dw = dt[qq] * zt[qq] * sg;                       // dt * silu(zt)
+          float dw = t_lin ? dt[qq] * zt[qq] : dt[qq] * zt[qq] * sg;              // dt * gamma_t: zt or silu(zt)
           if (gate) dw *= gate_df(htr_weight<LMAX>(qc, kc, y, nn, flags), gate);   // ... * gamma_w'(w)
           const float w = htr_weight_grad<LMAX, GY>(qc, kc, y, nn, flags, dw, gc, gy);
-          gz[qq] = dt[qq] * gate_f(w, gate) * sg * (1.0f + zt[qq] * (1.0f - sg));  // dt * gamma_w(w) * silu'(zt)
+          const float dact = t_lin ? 1.0f : sg * (1.0f + zt[qq] * (1.0f - sg));    // d gamma_t / d zt
+          gz[qq] = dt[qq] * gate_f(w, gate) * dact;
           amx = fmaxf(amx, fabsf(gz[qq]));
 #pragma unroll
           for (int m = 0; m < L; ++m) gq[m][qq] = gc[m];
@@ -364,7 +369,7 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
       float qc[L], gc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(gk, qq, gc);
-      float dw = dt[qq] * silu_fast_(zt[qq]);
+      float dw = (GATED && (flags & HTR_T_LINEAR)) ? dt[qq] * zt[qq] : dt[qq] * silu_fast_(zt[qq]);
       if (gate) {
         float kc[L];
         col_of<L, V>(kown, qq, kc);
@@ -402,7 +407,7 @@ using namespace goten;
 
 #define HTR_LAUNCH(KERNEL, LM, VV, T, ...)                                                      \
   do {                                                                                         \
-    if ((flags >> 2) & 3) KERNEL<LM, VV, true><<<N, T, 0, st>>>(__VA_ARGS__);                  \
+    if ((flags >> 2) & 7) KERNEL<LM, VV, true><<<N, T, 0, st>>>(__VA_ARGS__);                  \
     else KERNEL<LM, VV, false><<<N, T, 0, st>>>(__VA_ARGS__);                                  \
   } while (0)
 

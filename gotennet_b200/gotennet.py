@@ -65,15 +65,17 @@ class GATA(nn.Module):
         parts = edge_updates.split("_") if isinstance(edge_updates, str) and edge_updates else []
         if not all(p in _ALLOWED_UPDATE_PARTS for p in parts):
             raise ValueError(f"Invalid edge update parts. Allowed parts are {_ALLOWED_UPDATE_PARTS}")
-        unsupported = [p for p in parts if p not in ("norej", "gated", "gatedt", "act")]
+        unsupported = [p for p in parts if p not in ("norej", "gated", "gatedt", "act", "mlp", "mlpa")]
         if unsupported:
             raise NotImplementedError(f"edge_updates parts {unsupported} are outside the accelerated path")
         if aggr != "add":
             raise NotImplementedError("only aggr='add' is implemented in the fused message kernel")
         if edge_ln:
             raise NotImplementedError("edge_ln is outside the accelerated path")
-        if (evec_dim not in (None, n_atom_basis)) or (emlp_dim not in (None, n_atom_basis)):
-            raise NotImplementedError("evec_dim / emlp_dim different from n_atom_basis are not implemented")
+        if evec_dim not in (None, n_atom_basis):
+            raise NotImplementedError("evec_dim different from n_atom_basis needs the 'linw' edge update (not implemented)")
+        if emlp_dim is not None and emlp_dim % 4 != 0:
+            raise NotImplementedError("emlp_dim must be a multiple of 4 (16-byte rows of the edge projection buffer)")
         if not is_silu(activation):
             raise NotImplementedError("the fused kernels implement SiLU ('swish') only")
         if not 1 <= lmax <= 3:
@@ -82,8 +84,8 @@ class GATA(nn.Module):
         for name in ("gated", "gatedt", "act"):
             if name in parts:
                 gated = name
-        self.update_info = {"gated": gated, "rej": "norej" not in parts, "mlp": False, "mlpa": False, "lin_w": 0,
-                            "lin_ln": 0}
+        self.update_info = {"gated": gated, "rej": "norej" not in parts, "mlp": "mlp" in parts, "mlpa": "mlpa" in parts,
+                            "lin_w": 0, "lin_ln": 0}
         self.sep_htr, self.sep_dir, self.sep_tensor = sep_htr, sep_dir, sep_tensor
         self.epsilon, self.last_layer, self.edge_updates, self.scale_edge = epsilon, last_layer, edge_updates, scale_edge
         self.activation, self.dropout, self.n_atom_basis, self.lmax = activation, dropout, n_atom_basis, lmax
@@ -97,9 +99,14 @@ class GATA(nn.Module):
         self.W_k = mk(C, C, activation=None)
         self.gamma_v = nn.Sequential(mk(C, C, activation=activation), mk(C, multiplier * C, activation=None))
         self.W_re = mk(C, C, activation=activation)
-        self.edge_vec_dim = self.edge_mlp_dim = C
+        self.edge_vec_dim = C
+        self.edge_mlp_dim = C if emlp_dim is None else emlp_dim
         if not self.last_layer and self.edge_updates:
-            self.gamma_t = MLP([C, C], activation=activation, last_activation=self.activation, norm=edge_ln,
+            # gamma_t (reference :239-250): one Dense(C -> C, act), or with "mlp" / "mlpa" two layers through emlp_dim,
+            # the last one without ("mlp") or with ("mlpa") the activation
+            two = self.update_info["mlp"] or self.update_info["mlpa"]
+            self.gamma_t = MLP([C, self.edge_mlp_dim, C] if two else [C, C], activation=activation,
+                               last_activation=None if self.update_info["mlp"] else self.activation, norm=edge_ln,
                                weight_init=weight_init, bias_init=bias_init)
             self.W_vq = mk(C, C, activation=None, bias=False)
             if self.sep_htr:
@@ -154,7 +161,8 @@ class GATA(nn.Module):
         return {"H": self.num_heads, "lmax": self.lmax, "S": self.multiplier,
                 "gata_flags": (1 if self.sep_dir else 0) | (2 if self.sep_tensor else 0),
                 "htr_flags": (1 if self.sep_htr else 0) | (2 if self.update_info["rej"] else 0) |
-                             ({False: 0, "gated": 1, "gatedt": 2, "act": 3}[self.update_info["gated"]] << 2),
+                             ({False: 0, "gated": 1, "gatedt": 2, "act": 3}[self.update_info["gated"]] << 2) |
+                             (16 if self.update_info["mlp"] else 0),
                 "vk_groups": groups}
 
     def _block(self, plan: GraphPlan, h, Xd, t, Y, fc, kappa, t_amax=None, attn_drop_mask=None):
@@ -187,9 +195,12 @@ class GATA(nn.Module):
             We = torch.cat([self.W_re.weight, self.W_rs.weight], 0)
             be = torch.cat([self.W_re.bias, self.W_rs.bias], 0)
             Wvq = Wvk = None
+        Wt2 = bt2 = None
+        if self.has_htr and len(self.gamma_t.dense_layers) == 2:
+            Wt2, bt2 = self.gamma_t.dense_layers[1].weight, self.gamma_t.dense_layers[1].bias
         out = ops.GataBlockFn.apply(h, Xd, t, Y, fc, kappa, Wn1, bn1, self.gamma_s[1].weight, self.gamma_s[1].bias,
                                     self.gamma_v[1].weight, self.gamma_v[1].bias, We, be, Wvq, Wvk, plan,
-                                    self._kernel_cfg(), t_amax, drop)
+                                    self._kernel_cfg(), t_amax, drop, Wt2, bt2)
         if self.has_htr:
             return out
         return out[0], out[1], t, out[2]

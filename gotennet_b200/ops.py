@@ -434,9 +434,11 @@ class GataBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, plan, cfg, t_amax=None,
-                drop=None):
-        """drop [E,H] (optional): attention dropout factors mask / (1 - p) in plan edge order (gotennet.py:513)."""
-        _chk(h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, drop)
+                drop=None, Wt2=None, bt2=None):
+        """drop [E,H] (optional): attention dropout factors mask / (1 - p) in plan edge order (gotennet.py:513).
+        Wt2 [C,Em] / bt2 (optional): second layer of a two-layer gamma_t ("mlp" / "mlpa" edge updates, gotennet.py:239-250);
+        the last Em rows of We are then its first layer."""
+        _chk(h, Xd, t, Y, fc, kappa, Wn1, bn1, Ws2, bs2, Wv2, bv2, We, be, Wvq, Wvk, drop, Wt2, bt2)
         L_ = lib()
         st = _stream()
         N, C = h.shape
@@ -460,8 +462,15 @@ class GataBlockFn(torch.autograd.Function):
         gemm(A1, 2 * C, 0, Wv2, C, 1, v, SC, N, SC, C, bias=bv2, a_off=C, am=am)
         # edge projections (pre-activations; consumers apply SiLU)
         Ze = torch.empty(E, ldz, device=dev)
+        two = Wt2 is not None                       # two-layer gamma_t
+        Em = ldz - (S + 1) * C                      # width of gamma_t's first layer (0 on the last block)
+        A_t = torch.empty(E, Em, device=dev) if two else None   # SiLU of its pre-activation, input of the second layer
         if E > 0:
-            gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, am=am)
+            if two:
+                gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, act_out=A_t, ld_act=Em, act_lo=(S + 1) * C,
+                     act_hi=ldz, am=am)
+            else:
+                gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, am=am)
         h1 = torch.empty_like(h)
         Xd1 = torch.empty_like(Xd)
         alpha = torch.empty(E, H, device=dev)
@@ -484,14 +493,19 @@ class GataBlockFn(torch.autograd.Function):
                 gemm(Xd1, C, 0, Wqk, C, 1, EQK, 2 * C, rows, 2 * C, C, a_off=lo * N * C, b_off=g * 2 * C * C,
                      c_off=lo * N * 2 * C, am=am)
             t1 = torch.empty_like(t)
-            L_.call("goten_htr_fwd", _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, (S + 1) * C, _ptr(t),
+            Zt, ldt, zt0 = Ze, ldz, (S + 1) * C     # where the kernels read gamma_t's last pre-activation
+            if two:
+                Zt, ldt, zt0 = torch.empty(E, C, device=dev), C, 0
+                if E > 0:
+                    gemm(A_t, Em, 0, Wt2, Em, 1, Zt, C, E, C, Em, bias=bt2, am=am)
+            L_.call("goten_htr_fwd", _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Zt), ldt, zt0, _ptr(t),
                     _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(t1), _ptr(t1_amax), st)
         ctx.plan, ctx.cfg, ctx.htr = plan, cfg, htr
         amx = am.export([h, t, Wn1, Ws2, Wv2, We, Wqk, A1, Xd1 if htr else None])
         ctx.n_amax = len(amx)
-        ctx.has_drop = drop is not None
+        ctx.has_drop, ctx.two = drop is not None, two
         ctx.save_for_backward(h, Xd, t, Y, fc, kappa, Wn1, Ws2, Wv2, We, Wqk, Z1, A1, x, v, Ze, alpha, Xd1, EQK, *amx,
-                              *([drop] if drop is not None else []))
+                              *([drop] if drop is not None else []), *([A_t, Zt, Wt2] if two else []))
         ctx.mark_non_differentiable(hints)
         if htr:
             return h1, Xd1, t1, hints
@@ -508,6 +522,7 @@ class GataBlockFn(torch.autograd.Function):
         am = AmaxScope()
         am.load([h, t, Wn1, Ws2, Wv2, We, Wqk, A1, Xd1 if htr else None], saved[19:19 + ctx.n_amax])
         drop = saved[19 + ctx.n_amax] if ctx.has_drop else None
+        A_t, Zt2, Wt2 = saved[-3:] if ctx.two else (None, None, None)
         L_ = lib()
         st = _stream()
         N, C = h.shape
@@ -527,7 +542,7 @@ class GataBlockFn(torch.autograd.Function):
         am.put(gZe, gze_amax)
         g_Y = torch.zeros(E, L, device=dev) if need_gY else None
         g_fc = torch.zeros(E, device=dev) if need_gfc else None
-        dWvq = dWvk = None
+        dWvq = dWvk = dWt2 = dbt2 = None
         g_Xm = g_Xd1  # gradient reaching the post-message X
         if htr:
             if g_t1 is None:
@@ -536,12 +551,32 @@ class GataBlockFn(torch.autograd.Function):
             geqk_amax = am.slot(dev) if am.enabled else None
             am.put(g_EQK, geqk_amax)
             zt0 = (S + 1) * C
-            L_.call("goten_htr_bwd_tgt", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, zt0,
-                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(g_EQK), _ptr(gZe), ldz,
-                    _ptr(g_Y), _ptr(gze_amax), _ptr(geqk_amax), st)
-            L_.call("goten_htr_bwd_src", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Ze), ldz, zt0,
+            Zt, ldt, zc0, gZt, ldgt, gzt_amax = Ze, ldz, zt0, gZe, ldz, gze_amax
+            if ctx.two:  # gamma_t's last pre-activation and its gradient live in their own [E, C] buffers
+                Zt, ldt, zc0 = Zt2, C, 0
+                gZt, ldgt = torch.empty(E, C, device=dev), C
+                gzt_amax = am.slot(dev) if am.enabled else None
+                am.put(gZt, gzt_amax)
+            L_.call("goten_htr_bwd_tgt", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Zt), ldt, zc0,
+                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, lmax, cfg["htr_flags"], _ptr(g_EQK), _ptr(gZt), ldgt,
+                    _ptr(g_Y), _ptr(gzt_amax), _ptr(geqk_amax), st)
+            L_.call("goten_htr_bwd_src", _ptr(g_t1), _ptr(EQK), _ptr(EQK, C), 2 * C, _ptr(Y), _ptr(Zt), ldt, zc0,
                     _ptr(plan.src_ptr), _ptr(plan.src_perm), _ptr(plan.tgt), N, C, lmax, cfg["htr_flags"],
                     _ptr(g_EQK, C), _ptr(geqk_amax), st)
+            if ctx.two:  # back through gamma_t's second layer into the first layer's columns of gZe
+                Em = ldz - zt0
+                g_At = torch.empty(E, Em, device=dev)
+                dWt2 = torch.empty_like(Wt2)
+                dbt2 = torch.empty(C, device=dev)
+                if E > 0:
+                    gemm(gZt, C, 0, Wt2, Em, 0, g_At, Em, E, Em, C, am=am)
+                    gemm(gZt, C, 1, A_t, Em, 0, dWt2, Em, C, Em, E, colsum=dbt2, am=am)
+                    dsilu_mul(g_At, Em, 0, Ze, ldz, zt0, gZe, ldz, zt0, E, Em)
+                    if am.enabled:
+                        absmax(gZe, ldz, E, Em, a_off=zt0, out=gze_amax)
+                else:
+                    dWt2.zero_()
+                    dbt2.zero_()
             # X gradient: g_Xm^l = g_Xd1^l + [g_EQ | g_EK]^l [W_vq; W_vk,l] (one K = 2C GEMM per degree group, the
             # residual added once); weight gradients of the stacked weight, un-stacked below
             G = len(cfg["vk_groups"])
@@ -599,7 +634,7 @@ class GataBlockFn(torch.autograd.Function):
             dWe.zero_()
             dbe.zero_()
         return (g_h, g_Xd, g_t, g_Y, g_fc, None, dWn1, dbn1, dWs2, dbs2, dWv2, dbv2, dWe, dbe, dWvq, dWvk, None, None,
-                None, None)
+                None, None, dWt2 if ctx.two else None, dbt2 if ctx.two else None)
 
 
 # ---------------------------------------------------------------------------

@@ -240,6 +240,7 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
  * (ldp = 2C with EK = EQ + C when both projections come from one GEMM with the stacked
  * weight [W_vq; W_vk]).  flags bits 2-3: gamma_w of the gated edge updates (0 identity,
  * 1 sigmoid "gated", 2 tanh "gatedt", 3 SiLU "act"; gotennet.py:283-289).
+ * bit 4: gamma_t ends without activation ("mlp" edge update): zt is used as is.
  * flags: bit0 = sep_htr (rejection per degree),
  * bit1 = rejection enabled.                                                    */
 int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,

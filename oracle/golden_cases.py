@@ -61,6 +61,13 @@ for _i, _flag in enumerate(["gated", "gatedt_norej", "act"]):
                                                       num_heads=4, sep_dir=True, sep_tensor=True, scale_edge=bool(_i % 2),
                                                       edge_updates=_flag), atoms=[11, 7], seed=13 + _i)
 
+# two-layer gamma_t: "mlp" (no final activation, emlp_dim 48) and "mlpa" combined with a gate
+NORM_CASES["eu_mlp"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, num_heads=4, sep_dir=True,
+                                             sep_tensor=True, scale_edge=False, edge_updates="mlp", emlp_dim=48),
+                            atoms=[10, 9], seed=16)
+NORM_CASES["eu_mlpa_gated"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=3, lmax=1, num_heads=4,
+                                                    edge_updates="mlpa_gated"), atoms=[13, 4], seed=17)
+
 # read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
 # representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
 HEAD_CASES = {

@@ -54,6 +54,7 @@ class OracleConfig:
     sep_dir: bool = False
     sep_tensor: bool = False
     max_num_neighbors: int = 32
+    emlp_dim: Optional[int] = None  # width of gamma_t's hidden layer with the "mlp" / "mlpa" edge updates (:236-242)
     radial_basis: str = "expnorm"   # "expnorm" | "BesselBasis" | "GaussianRBF" (layers.py:749-777)
     layernorm: str = ""        # != "": nn.LayerNorm on h at the top of every GATA block (gotennet.py:308-310, :397)
     steerable_norm: str = ""   # != "": TensorLayerNorm on X (gotennet.py:311-315, :398)
@@ -120,8 +121,16 @@ def state_dict_spec(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]
         if cfg.steerable_norm:
             sp.append((p + "tensor_layernorm.weight", (C,), "ln_w"))   # a buffer in the reference (trainable=False)
         if not last and cfg.edge_updates:
-            sp.append((p + "gamma_t.dense_layers.0.weight", (C, C), "weight"))
-            sp.append((p + "gamma_t.dense_layers.0.bias", (C,), "bias"))
+            eu = cfg.edge_updates.split("_") if isinstance(cfg.edge_updates, str) else []
+            if "mlp" in eu or "mlpa" in eu:                            # two-layer gamma_t, gotennet.py:239-250
+                Em = cfg.emlp_dim or C
+                sp.append((p + "gamma_t.dense_layers.0.weight", (Em, C), "weight"))
+                sp.append((p + "gamma_t.dense_layers.0.bias", (Em,), "bias"))
+                sp.append((p + "gamma_t.dense_layers.1.weight", (C, Em), "weight"))
+                sp.append((p + "gamma_t.dense_layers.1.bias", (C,), "bias"))
+            else:
+                sp.append((p + "gamma_t.dense_layers.0.weight", (C, C), "weight"))
+                sp.append((p + "gamma_t.dense_layers.0.bias", (C,), "bias"))
             sp.append((p + "W_vq.weight", (C, C), "weight"))
             if cfg.sep_htr:
                 for l in range(cfg.lmax):
@@ -416,7 +425,12 @@ def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges
             w = torch.tanh(w)
         elif "gated" in parts:
             w = torch.sigmoid(w)
-        t = t + F.silu(_lin(sd, p + "gamma_t.dense_layers.0", t)) * w  # :611, :445
+        gt = F.silu(_lin(sd, p + "gamma_t.dense_layers.0", t))
+        if "mlp" in parts or "mlpa" in parts:                          # MLP([C, emlp, C]), last activation None for "mlp"
+            gt = _lin(sd, p + "gamma_t.dense_layers.1", gt)
+            if "mlp" not in parts:
+                gt = F.silu(gt)
+        t = t + gt * w                                                 # :611, :445
     return h, X, t
 
 

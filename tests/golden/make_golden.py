@@ -42,7 +42,7 @@ def build_reference(ref, cfg: orc.OracleConfig):
         attn_dropout=0.0, edge_updates=cfg.edge_updates, scale_edge=cfg.scale_edge, lmax=cfg.lmax,
         sep_htr=cfg.sep_htr, sep_dir=cfg.sep_dir, sep_tensor=cfg.sep_tensor,
         max_num_neighbors=cfg.max_num_neighbors, layernorm=cfg.layernorm, steerable_norm=cfg.steerable_norm,
-        radial_basis=cfg.radial_basis,
+        radial_basis=cfg.radial_basis, emlp_dim=cfg.emlp_dim,
     )
 
 

@@ -66,7 +66,7 @@ def test_constructor_errors(g):
     with pytest.raises(ValueError):
         g.GATA(64, torch.nn.functional.silu, edge_updates="bogus")  # gotennet.py:164-167
     with pytest.raises(NotImplementedError):
-        g.GATA(64, torch.nn.functional.silu, edge_updates="mlp")
+        g.GATA(64, torch.nn.functional.silu, edge_updates="linw")
     assert isinstance(g.GATA(64, torch.nn.functional.silu, edge_updates="gated_gatedt").gamma_w[0], torch.nn.Tanh)
     m = g.GotenNet(n_atom_basis=32, n_interactions=1, cutoff_fn=g.CosineCutoff(5.0), radial_basis="BesselBasis", n_rbf=8)
     assert set(k for k in m.state_dict() if k.startswith("radial_basis.")) == {"radial_basis.freqs", "radial_basis.norm1"}
