@@ -148,3 +148,60 @@ def test_collate_ragged_molecules(g):
     with pytest.raises(ValueError):
         g.collate([([1, 1], [[0, 0, 0]])])
     assert g.collate([]).num_graphs == 0
+
+
+def test_force_matching_algorithm_on_a_torch_model(g):
+    """The central-difference force-matching step (gotennet_b200/training.py) is model-agnostic host logic: on a small
+    float64 PyTorch energy model its parameter gradient equals the exact double backward through the forces."""
+    torch.manual_seed(0)
+
+    class Rep(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.lin = torch.nn.Linear(3, 8).double()
+
+        def forward(self, d):
+            r = d.pos - d.pos.mean(0, keepdim=True)
+            return torch.tanh(self.lin(r)) * r.pow(2).sum(1, keepdim=True), None
+
+    class Head(torch.nn.Module):
+        property, derivative = "y", None
+
+        def __init__(self):
+            super().__init__()
+            self.out = torch.nn.Linear(8, 1).double()
+
+        def forward(self, d):
+            yi = self.out(d.representation)
+            return {"y": torch.zeros(2, 1, dtype=yi.dtype).index_add_(0, d.batch, yi)}
+
+    rep, head = Rep(), Head()
+
+    class D:
+        pass
+
+    d = D()
+    d.z, d.batch = torch.ones(7, dtype=torch.long), torch.tensor([0, 0, 0, 1, 1, 1, 1])
+    d.pos = torch.randn(7, 3, dtype=torch.float64)
+    E_t, F_t = torch.randn(2, 1, dtype=torch.float64), torch.randn(7, 3, dtype=torch.float64)
+    loss_fn = lambda E, F: (E - E_t).pow(2).mean() + 3.0 * (F - F_t).pow(2).mean()  # noqa: E731
+    # exact
+    pos = d.pos.clone().requires_grad_(True)
+    dd = D()
+    dd.z, dd.batch, dd.pos = d.z, d.batch, pos
+    dd.representation, _ = rep(dd)
+    E = head(dd)["y"]
+    (gp,) = torch.autograd.grad(E.sum(), pos, create_graph=True)
+    loss_fn(E, -gp).backward()
+    params = list(rep.parameters()) + list(head.parameters())
+    exact = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    for order, tol in ((4, 1e-7), (2, 1e-4)):
+        loss, E2, F2 = g.force_matching_backward(rep, head, d, loss_fn, h=1e-3, order=order)
+        assert torch.allclose(E2, E.detach()) and torch.allclose(F2, -gp.detach())
+        for p, e in zip(params, exact):
+            assert (p.grad - e).abs().max() <= tol * e.abs().max(), (order, (p.grad - e).abs().max() / e.abs().max())
+            p.grad = None
+    with pytest.raises(ValueError):
+        g.force_matching_backward(rep, head, d, loss_fn, order=3)
