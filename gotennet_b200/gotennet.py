@@ -209,21 +209,22 @@ class GATA(nn.Module):
                 n_edges: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
         """Stand-alone layer call with the reference signature (gotennet.py:366-375):
         h [N,1,C], X [N,L,C], rl_ij [E,L], t_ij [E,C], r_ij [E], n_edges [E] -> (h, X, t_ij)."""
-        N, C = h.shape[0], self.n_atom_basis
-        plan = plan_from_edge_index(edge_index, N)
-        rl, t, r, ne = rl_ij.reshape(plan.E, -1), t_ij.reshape(plan.E, C), r_ij.reshape(-1), n_edges.reshape(-1)
-        if plan.order is not None:
-            rl, t, r, ne = rl[plan.order], t[plan.order], r[plan.order], ne[plan.order]
-        fc = self.cutoff(r).contiguous()
-        kappa = (torch.sqrt(ne.float()) if self.scale_edge else torch.ones_like(r)) / (C ** 0.5)
-        Xd = ops.PermuteFn.apply(X, True)
-        h1, Xd1, t1, _ = self._block(plan, h.reshape(N, C).contiguous(), Xd, t.contiguous(), rl.contiguous().float(), fc,
-                                  kappa.contiguous())
-        if plan.order is not None:
-            inv = torch.empty_like(plan.order)
-            inv[plan.order] = torch.arange(plan.E, device=inv.device)
-            t1 = t1[inv]
-        return h1.unsqueeze(1), ops.PermuteFn.apply(Xd1, False), t1
+        with ops.device_of(h):
+            N, C = h.shape[0], self.n_atom_basis
+            plan = plan_from_edge_index(edge_index, N)
+            rl, t, r, ne = rl_ij.reshape(plan.E, -1), t_ij.reshape(plan.E, C), r_ij.reshape(-1), n_edges.reshape(-1)
+            if plan.order is not None:
+                rl, t, r, ne = rl[plan.order], t[plan.order], r[plan.order], ne[plan.order]
+            fc = self.cutoff(r).contiguous()
+            kappa = (torch.sqrt(ne.float()) if self.scale_edge else torch.ones_like(r)) / (C ** 0.5)
+            Xd = ops.PermuteFn.apply(X, True)
+            h1, Xd1, t1, _ = self._block(plan, h.reshape(N, C).contiguous(), Xd, t.contiguous(),
+                                         rl.contiguous().float(), fc, kappa.contiguous())
+            if plan.order is not None:
+                inv = torch.empty_like(plan.order)
+                inv[plan.order] = torch.arange(plan.E, device=inv.device)
+                t1 = t1[inv]
+            return h1.unsqueeze(1), ops.PermuteFn.apply(Xd1, False), t1
 
 
 class EQFF(nn.Module):
@@ -251,9 +252,10 @@ class EQFF(nn.Module):
 
     def forward(self, h: Tensor, X: Tensor) -> Tuple[Tensor, Tensor]:
         """h [N,1,C], X [N,L,C] -> same shapes."""
-        N, C = h.shape[0], self.n_atom_basis
-        h2, Xd2 = self._block(h.reshape(N, C).contiguous(), ops.PermuteFn.apply(X, True))
-        return h2.unsqueeze(1), ops.PermuteFn.apply(Xd2, False)
+        with ops.device_of(h):
+            N, C = h.shape[0], self.n_atom_basis
+            h2, Xd2 = self._block(h.reshape(N, C).contiguous(), ops.PermuteFn.apply(X, True))
+            return h2.unsqueeze(1), ops.PermuteFn.apply(Xd2, False)
 
 
 class GotenNet(nn.Module):
@@ -344,7 +346,18 @@ class GotenNet(nn.Module):
         return ops.EdgeGeometryFn.apply(pos, edge_vec, edge_diff, p0.float().contiguous(), p1.float().contiguous(), plan,
                                         self.sphere.l, self.cutoff, self.scale_edge, self.n_atom_basis, basis)
 
-    def _core(self, z: Tensor, plan: GraphPlan, Y, fc, kappa, phi) -> Tuple[Tensor, Tensor]:
+    def draw_attn_drop_masks(self, plan: GraphPlan) -> Optional[List[Tensor]]:
+        """Per-layer attention dropout factors keep / (1 - p), [E, H] in plan edge order, drawn from torch's CUDA
+        generator (reference gotennet.py:513 F.dropout); None in eval mode or with attn_dropout = 0.  Passing the result
+        back through `forward(..., attn_drop_masks=...)` repeats the SAME stochastic network (training.py needs that for
+        its stencil passes)."""
+        if not self.training or not any(g.dropout > 0 for g in self.gata_list):
+            return None
+        dev = plan.src.device
+        return [((torch.rand(plan.E, g.num_heads, device=dev) >= g.dropout).float() / (1.0 - g.dropout))
+                if g.dropout > 0 else None for g in self.gata_list]
+
+    def _core(self, z: Tensor, plan: GraphPlan, Y, fc, kappa, phi, attn_drop_masks=None) -> Tuple[Tensor, Tensor]:
         C, L = self.n_atom_basis, self.sphere.tensor_size
         z = z.contiguous().long()
         ni, ei = self.node_init, self.edge_init
@@ -361,7 +374,8 @@ class GotenNet(nn.Module):
             cap.update(h0=h.detach(), t0=t.detach(), Y=Y.detach(), phi=phi.detach(), fc=fc.detach())
         for i, (gata, eqff) in enumerate(zip(self.gata_list, self.eqff_list)):
             has_htr = gata.has_htr
-            h, Xd, t, hints = gata._block(plan, h, Xd, t, Y, fc, kappa, t_amax)
+            h, Xd, t, hints = gata._block(plan, h, Xd, t, Y, fc, kappa, t_amax,
+                                          attn_drop_masks[i] if attn_drop_masks is not None else None)
             t_amax = hints[1:2] if has_htr else t_amax
             h, Xd = eqff._block(h, Xd, hints[0:1])
             if cap is not None:
@@ -372,18 +386,20 @@ class GotenNet(nn.Module):
     def forward(self, atomic_numbers, edge_index, edge_diff, edge_vec) -> Tuple[Tensor, Tensor]:
         """atomic_numbers [N], edge_index [2,E], edge_diff [E], edge_vec [E,3] -> (h [N,C], X [N,L,C]).
         As in the reference (gotennet.py:978-980) `edge_vec` is normalised IN PLACE on non-loop edges."""
-        plan = plan_from_edge_index(edge_index, atomic_numbers.shape[0])
-        ev, ed = edge_vec, edge_diff.reshape(-1)
-        if plan.order is not None:
-            ev, ed = ev[plan.order], ed[plan.order]
-        r, Y, fc, phi, u, kappa = self._geometry(plan, edge_vec=ev.contiguous().float(), edge_diff=ed.contiguous().float())
-        if not edge_vec.requires_grad:
-            with torch.no_grad():
-                if plan.order is not None:
-                    edge_vec[plan.order] = u
-                else:
-                    edge_vec.copy_(u)
-        return self._core(atomic_numbers, plan, Y, fc, kappa, phi)
+        with ops.device_of(edge_index):
+            plan = plan_from_edge_index(edge_index, atomic_numbers.shape[0])
+            ev, ed = edge_vec, edge_diff.reshape(-1)
+            if plan.order is not None:
+                ev, ed = ev[plan.order], ed[plan.order]
+            r, Y, fc, phi, u, kappa = self._geometry(plan, edge_vec=ev.contiguous().float(),
+                                                     edge_diff=ed.contiguous().float())
+            if not edge_vec.requires_grad:
+                with torch.no_grad():
+                    if plan.order is not None:
+                        edge_vec[plan.order] = u
+                    else:
+                        edge_vec.copy_(u)
+            return self._core(atomic_numbers, plan, Y, fc, kappa, phi)
 
 
 class GotenNetWrapper(GotenNet):
@@ -395,9 +411,16 @@ class GotenNetWrapper(GotenNet):
         self.distance = Distance(self.cutoff, max_num_neighbors=max_num_neighbors, loop=True)
         self.reset_parameters()
 
-    def forward(self, inputs: Mapping[str, Tensor]) -> Tuple[Tensor, Tensor]:
+    def forward(self, inputs: Mapping[str, Tensor], plan: Optional[GraphPlan] = None,
+                attn_drop_masks: Optional[List[Tensor]] = None) -> Tuple[Tensor, Tensor]:
+        """`inputs.z / .pos / .batch` -> (h [N,C], X [N,L,C]) (reference gotennet.py:1026-1045).
+        Two optional extensions (not in the reference signature, defaults reproduce it): `plan` = a GraphPlan built
+        earlier (`self.distance.plan(pos, batch)`) to keep the edge set fixed while positions move, and
+        `attn_drop_masks` = the per-layer dropout factors of `draw_attn_drop_masks`."""
         z, pos, batch = inputs.z, inputs.pos, inputs.batch
-        plan = self.distance.plan(pos, batch)
-        r, Y, fc, phi, u, kappa = self._geometry(plan, pos=pos.contiguous().float())
-        self.last_plan = plan
-        return self._core(z, plan, Y, fc, kappa, phi)
+        with ops.device_of(pos):
+            if plan is None:
+                plan = self.distance.plan(pos, batch)
+            r, Y, fc, phi, u, kappa = self._geometry(plan, pos=pos.contiguous().float())
+            self.last_plan = plan
+            return self._core(z, plan, Y, fc, kappa, phi, attn_drop_masks)

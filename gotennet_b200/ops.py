@@ -14,6 +14,7 @@ our control.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 from typing import Optional
 
@@ -35,6 +36,12 @@ def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
+def device_of(t: torch.Tensor):
+    """Context manager making t's CUDA device current (the C ABI launches on the current device's stream); a no-op
+    for CPU tensors, which the kernels reject further down with GotenError."""
+    return torch.cuda.device(t.device) if t.is_cuda else contextlib.nullcontext()
+
+
 def _ptr(t: Optional[torch.Tensor], off: int = 0):
     if t is None:
         return None
@@ -42,11 +49,18 @@ def _ptr(t: Optional[torch.Tensor], off: int = 0):
 
 
 def _chk(*ts):
+    cur = None
     for t in ts:
         if t is None:
             continue
         if not t.is_cuda:
             raise GotenError("gotennet_b200 kernels need CUDA tensors (there is no CPU path)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the C ABI launches on the current device's stream; a foreign pointer there would fault
+            raise GotenError(f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}: call the module "
+                             "entry points (they select the device) or wrap the call in torch.cuda.device(...)")
         if not t.is_contiguous():
             raise GotenError("non-contiguous tensor passed to a kernel")
 

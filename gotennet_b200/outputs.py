@@ -99,6 +99,22 @@ class SchnetMLP(nn.Module):
         return x
 
 
+class _FirstOrderOnly(torch.autograd.Function):
+    """Identity on a derivative computed by the first-order kernels; differentiating through it raises."""
+
+    @staticmethod
+    def forward(ctx, dy, pos, name):
+        ctx.name = name
+        return dy.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        raise GotenError(
+            f"back-propagating through '{ctx.name}' needs second-order kernels, which gotennet_b200 does not have: "
+            "train force-matching losses with gotennet_b200.force_matching_backward(model, head, batch, loss_fn) "
+            "(head built with derivative=None), or detach the derivative")
+
+
 _MODES = {None: 0, "sum": 1, "add": 1, "mean": 2, "avg": 2}
 
 
@@ -131,6 +147,10 @@ class Atomwise(nn.Module):
 
     def forward(self, inputs):
         z = inputs.z
+        with ops.device_of(z):
+            return self._forward(inputs, z)
+
+    def _forward(self, inputs, z):
         result = {}
         raw = self.out_net(inputs)  # [N, n_out]
         if not raw.is_cuda:
@@ -151,9 +171,15 @@ class Atomwise(nn.Module):
         if self.contributions:
             result[self.contributions] = yi
         if self.derivative:
+            # The kernels are first-order: the derivative is taken WITHOUT building a second-order graph, whatever
+            # `create_graph` says (reference outputs.py:365-375 defaults to True).  The returned tensor still joins
+            # the autograd graph through _FirstOrderOnly, whose backward raises a pointed error instead of the
+            # anonymous "once_differentiable" failure deep inside a training step.
             sign = -1.0 if self.negative_dr else 1.0
             dy = grad(outputs=result[self.property], inputs=[inputs.pos],
-                      grad_outputs=torch.ones_like(result[self.property]), create_graph=self.create_graph,
-                      retain_graph=True)[0]
-            result[self.derivative] = sign * dy
+                      grad_outputs=torch.ones_like(result[self.property]), create_graph=False, retain_graph=True)[0]
+            dy = sign * dy
+            if self.create_graph and torch.is_grad_enabled() and inputs.pos.requires_grad:
+                dy = _FirstOrderOnly.apply(dy, inputs.pos, self.derivative)
+            result[self.derivative] = dy
         return result

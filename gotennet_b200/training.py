@@ -38,35 +38,59 @@ def _with_pos(batch, pos):
     return d
 
 
-def _energy(model, head, batch, pos):
+def _energy(model, head, batch, pos, plan=None, masks=None):
     d = _with_pos(batch, pos)
-    d.representation, d.vector_representation = model(d)
+    if plan is not None or masks is not None:
+        d.representation, d.vector_representation = model(d, plan=plan, attn_drop_masks=masks)
+    else:
+        d.representation, d.vector_representation = model(d)
     return head(d)[head.property]
 
 
-def energy_and_forces(model, head, batch) -> Tuple[torch.Tensor, torch.Tensor]:
+def _frozen_network(model, batch, attn_drop_masks=None):
+    """(plan, masks) that pin the stochastic / discrete parts of one training step: the radius graph built at the base
+    positions (the reference's exact double backward differentiates at FIXED topology: edge set, softmax support and
+    out-degrees do not move with the positions) and ONE draw of the per-layer attention-dropout factors shared by every
+    pass of the step.  Models without the GotenNetWrapper extensions get (None, None) and are called plainly."""
+    if not (hasattr(model, "distance") and hasattr(model, "draw_attn_drop_masks")):
+        if attn_drop_masks is not None:
+            raise ValueError("attn_drop_masks need a GotenNetWrapper")
+        return None, None
+    plan = model.distance.plan(batch.pos.detach(), batch.batch)
+    masks = attn_drop_masks if attn_drop_masks is not None else model.draw_attn_drop_masks(plan)
+    return plan, masks
+
+
+def energy_and_forces(model, head, batch, attn_drop_masks=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """E [n_mol, n_out] and F = -dE_total/dpos [N, 3] (first order, detached)."""
     pos = batch.pos.detach().clone().requires_grad_(True)
-    E = _energy(model, head, batch, pos)
+    E = _energy(model, head, batch, pos, None, attn_drop_masks)
     (g,) = torch.autograd.grad(E.sum(), pos)
     return E.detach(), -g
 
 
 def force_matching_backward(model, head, batch, loss_fn: Callable[[torch.Tensor, torch.Tensor], torch.Tensor],
-                            params: Optional[Iterable[torch.nn.Parameter]] = None, h: float = 2.5e-3, order: int = 4):
+                            params: Optional[Iterable[torch.nn.Parameter]] = None, h: float = 2.5e-3, order: int = 4,
+                            attn_drop_masks=None):
     """Accumulates d loss_fn(E, F) / d theta into `.grad` of the parameters (model + head unless `params` is given)
     and returns (loss, E, F) detached.  `head` must not compute derivatives itself (derivative=None).
     `h` is the largest atomic displacement (in the units of pos) of the inner stencil points; the default balances
     truncation (the energy surface has large higher derivatives: h = 1e-2 is already 10 % off) against fp32 round-off
-    (measured with the fp32 oracle: worst parameter tensor 3e-4, median 4e-5 at h = 2.5e-3)."""
+    (measured with the fp32 oracle: worst parameter tensor 3e-4, median 4e-5 at h = 2.5e-3).
+    All passes of one call run the SAME network: the radius graph is built once at the base positions and reused by the
+    displaced passes, and in training mode with attn_dropout > 0 the per-layer dropout factors are drawn once
+    (`attn_drop_masks`: supply them to reproduce a step; the ones used are left in `model.last_attn_drop_masks`)."""
     if order not in (2, 4):
         raise ValueError("order must be 2 or 4")
     if getattr(head, "derivative", None):
         raise ValueError("use a head without derivative=...: the forces are formed here")
     params = [p for p in (params if params is not None else list(model.parameters()) + list(head.parameters()))
               if p.requires_grad]
+    plan, masks = _frozen_network(model, batch, attn_drop_masks)
+    if plan is not None:
+        model.last_attn_drop_masks = masks
     pos0 = batch.pos.detach().clone().requires_grad_(True)
-    E = _energy(model, head, batch, pos0)
+    E = _energy(model, head, batch, pos0, plan, masks)
     (gpos,) = torch.autograd.grad(E.sum(), pos0, retain_graph=True)
     F = -gpos
     E_leaf, F_leaf = E.detach().requires_grad_(True), F.detach().requires_grad_(True)
@@ -94,7 +118,7 @@ def force_matching_backward(model, head, batch, loss_fn: Callable[[torch.Tensor,
         base = batch.pos.detach()
 
         def G(s):
-            return grads_of(lambda: _energy(model, head, batch, base + s * h * uhat).sum().backward())
+            return grads_of(lambda: _energy(model, head, batch, base + s * h * uhat, plan, masks).sum().backward())
 
         gp, gm = G(1.0), G(-1.0)
         if order == 2:

@@ -539,12 +539,13 @@ def atomwise_forward(sd: Dict[str, Tensor], h: Tensor, z: Tensor, batch: Tensor,
     return y, yi
 
 
-def energy_and_forces(sd, sd_head, cfg: OracleConfig, z, pos, batch, n_mol: int, activation: str = "silu"):
+def energy_and_forces(sd, sd_head, cfg: OracleConfig, z, pos, batch, n_mol: int, activation: str = "silu",
+                      drop_masks=None):
     """Representation + Atomwise(derivative=..., negative_dr=True) (goten_model.py:289, outputs.py:365-375):
     E [n_mol,1] and F = -dE/dpos [N,3] (differentiable: create_graph=True)."""
     if not pos.requires_grad:
         pos = pos.clone().requires_grad_(True)
-    h, X = wrapper_forward(sd, cfg, z, pos, batch)
+    h, X = wrapper_forward(sd, cfg, z, pos, batch, drop_masks=drop_masks)
     y, yi = atomwise_forward(sd_head, h, z, batch, n_mol, activation)
     (dy,) = torch.autograd.grad(y, [pos], grad_outputs=torch.ones_like(y), create_graph=True, retain_graph=True)
     return y, -dy, h

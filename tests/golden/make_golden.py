@@ -46,7 +46,8 @@ def build_reference(ref, cfg: orc.OracleConfig):
     )
 
 
-def run_case(ref, name, spec):
+def run_case(ref, name, spec, save=True):
+    """Runs one case on the verbatim reference; returns the fixture dict (and writes <name>.npz when `save`)."""
     cfg = spec["cfg"]
     z, pos, batch = _blob(spec["atoms"], spec["seed"])
     sd = orc.make_state_dict(cfg, seed=spec["seed"])
@@ -122,7 +123,9 @@ def run_case(ref, name, spec):
     print(f"{name}: N={z.numel()} E={captured['edge_index'].shape[1]} oracle-vs-reference rel err "
           f"h {err_h:.2e} X {err_X:.2e} dpos {err_p:.2e} dparam {worst_g:.2e}")
     assert max(err_h, err_X, err_p) < 2e-5 and worst_g < 1e-4, name
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    if save:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    return out
 
 
 def main():

@@ -27,7 +27,7 @@ sys.path.insert(0, HERE)
 from make_golden import build_reference  # noqa: E402
 
 
-def run_case(ref, name, spec):
+def run_case(ref, name, spec, save=True):
     from gotennet.models.components.layers import shifted_softplus
     from gotennet.models.components.outputs import Atomwise
 
@@ -88,7 +88,9 @@ def run_case(ref, name, spec):
             worst = max(worst, rel(grad_fingerprint(g if g is not None else torch.zeros_like(sdo[k[5:]])), torch.from_numpy(out[k])))
     print(f"{name}: N={z.numel()} oracle-vs-reference rel err E {rel(Eo, E):.2e} F {rel(Fo_o, Fo):.2e} dparam {worst:.2e}")
     assert rel(Eo, E) < 2e-6 and rel(Fo_o, Fo) < 2e-5 and worst < 1e-4, name
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    if save:
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    return out
 
 
 def main():

@@ -283,6 +283,75 @@ def test_rmd17_and_md22_shapes_vs_oracle(g, dev):
         assert rel(d.pos.grad, pos_o.grad) < TOL, kind
 
 
+
+def _oracle_leaf_state(sd):
+    return {k: v.clone().requires_grad_(v.is_floating_point() and "radial_basis" not in k) for k, v in sd.items()}
+
+
+def _assert_param_grads(params, sdo, keys, what):
+    """every parameter gradient against the oracle's autograd, each tensor at the 1e-4 bar"""
+    n = 0
+    for k in keys:
+        gr = params[k].grad if params[k].grad is not None else torch.zeros_like(params[k])
+        go = sdo[k].grad if sdo[k].grad is not None else torch.zeros_like(sdo[k])
+        assert rel(gr, go) < TOL, (what, k, rel(gr, go))
+        n += 1
+    return n
+
+
+def test_cfg4_production_width_vs_oracle(g, dev):
+    """BASELINE configs[3] at production width: C=256, 4 interactions, lmax=3 (L=15, S=7), K=160, one 370-atom
+    MD22-shape molecule (in-degree up to ~134: the chunked d-alpha sums, the <3,1,1> instantiations, the 2-channel HTR
+    backward).  h, X, d/dpos and EVERY parameter gradient against the CPU oracle (reference gotennet.py:956-1010)."""
+    cfg = orc.OracleConfig(n_atom_basis=256, n_interactions=4, lmax=3, sep_dir=True, sep_tensor=True,
+                           scale_edge=False, max_num_neighbors=160)
+    z, pos, batch = orc.synth_batch("md22", 1, seed=5)
+    sd = orc.make_state_dict(cfg, seed=1)
+    m = build(g, cfg, sd, dev)
+    d = make_data(z, pos, batch, dev)
+    h, X = m(d)
+    (h.sum() + X.pow(2).sum()).backward()
+    assert int((m.last_plan.tgt_ptr[1:] - m.last_plan.tgt_ptr[:-1]).max()) > 64  # the long-neighbour-list regime
+    sdo = _oracle_leaf_state(sd)
+    pos_o = pos.clone().requires_grad_(True)
+    inter = {}
+    ho, Xo = orc.wrapper_forward(sdo, cfg, z, pos_o, batch, inter)
+    (ho.sum() + Xo.pow(2).sum()).backward()
+    assert torch.equal(m.last_plan.edge_index.cpu(), inter["edge_index"])
+    assert rel(h.detach(), ho.detach()) < TOL and rel(X.detach(), Xo.detach()) < TOL
+    assert rel(d.pos.grad, pos_o.grad) < TOL
+    keys = [k for k, _, _ in orc.state_dict_spec(cfg)]
+    assert _assert_param_grads(dict(m.named_parameters()), sdo, keys, "cfg4") == len(keys)
+
+
+def test_cfg3_production_width_forces_vs_oracle(g, dev):
+    """BASELINE configs[2] at production width: C=256, 6 interactions, lmax=2, aspirin-shape molecules, Atomwise energy
+    head with derivative='forces' (reference outputs.py:323-376).  Energy, forces and every representation / head
+    parameter gradient of (E * w).sum() against the CPU oracle."""
+    cfg = orc.OracleConfig(n_atom_basis=256, n_interactions=6, lmax=2, sep_dir=True, sep_tensor=True, scale_edge=False)
+    n_mol = 4
+    z, pos, batch = orc.synth_batch("aspirin", n_mol, seed=5)
+    sd = orc.make_state_dict(cfg, seed=2)
+    sdh = orc.make_head_state_dict(cfg.n_atom_basis, seed=2)
+    rep = build(g, cfg, sd, dev)
+    head = build_head(g, cfg, sdh, "silu", dev, derivative="forces")
+    d = DataNS()
+    d.z, d.pos, d.batch, d.num_graphs = z.to(dev), pos.to(dev).requires_grad_(True), batch.to(dev), n_mol
+    d.representation, d.vector_representation = rep(d)
+    res = head(d)
+    w = probe_vector(n_mol).unsqueeze(1)
+    ((res["property"] * w.to(dev)).sum()).backward()
+    sdo = _oracle_leaf_state(sd)
+    sdho = {k: v.clone().requires_grad_(k.startswith("out_net")) for k, v in sdh.items()}
+    Eo, Fo, _ = orc.energy_and_forces(sdo, sdho, cfg, z, pos, batch, n_mol, "silu")
+    ((Eo * w).sum()).backward()
+    assert rel(res["property"].detach(), Eo.detach()) < TOL
+    assert rel(res["forces"].detach(), Fo.detach()) < TOL
+    keys = [k for k, _, _ in orc.state_dict_spec(cfg)]
+    _assert_param_grads(dict(rep.named_parameters()), sdo, keys, "cfg3 representation")
+    _assert_param_grads(dict(head.named_parameters()), sdho, [k for k in sdho if k.startswith("out_net")], "cfg3 head")
+
+
 # ------------------------------------------------- API surface parity ----------
 def test_external_edge_index_and_blocks(g, dev):
     """GotenNet.forward with a caller-supplied (shuffled) edge list, in-place edge_vec normalisation,
@@ -468,8 +537,35 @@ def test_fused_adamw_matches_torch(g, dev, clip):
         assert abs(float(ours.grad_norm) - float(total)) <= 1e-5 * float(total)
         for p, q in zip(ref_p, our_p):
             assert rel(q.data, p.data) < 2e-6
-    sd = ours.state_dict()
-    assert sd["step"] == 6 and sd["exp_avg"].numel() == ours.flat_p.numel()
+    # torch.optim surface: an Optimizer subclass with torch-format state, closure-taking step, schedulers
+    assert isinstance(ours, torch.optim.Optimizer) and ours.defaults["eps"] == 1e-7
+    sd, sd_ref = ours.state_dict(), ref.state_dict()
+    assert set(sd) == set(sd_ref) == {"state", "param_groups"}
+    assert sorted(sd["state"]) == sorted(sd_ref["state"]) and float(sd["state"][0]["step"]) == 6.0
+    for i in sd_ref["state"]:
+        assert rel(sd["state"][i]["exp_avg"], sd_ref["state"][i]["exp_avg"]) < 2e-6
+        assert rel(sd["state"][i]["exp_avg_sq"], sd_ref["state"][i]["exp_avg_sq"]) < 2e-6
+    torch.optim.lr_scheduler.ReduceLROnPlateau(ours, factor=0.8, patience=15)   # goten_model.py:536-541
+    torch.optim.lr_scheduler.CosineAnnealingLR(ours, T_max=10)                  # goten_model.py:543-545
+    # resume: a fresh FusedAdamW loaded from torch.optim.AdamW's own state_dict continues identically
+    our_p2 = [torch.nn.Parameter(p.detach().clone().to(dev)) for p in ref_p]
+    ours2 = g.FusedAdamW(our_p2, lr=3e-3, weight_decay=0.05, eps=1e-7, max_grad_norm=clip)
+    ours2.load_state_dict(sd_ref)
+    grads = [torch.randn(*s_, generator=gen) for s_ in shapes]
+    for p_, q_, gr in zip(ref_p, our_p2, grads):
+        p_.grad = gr.clone()
+    if clip:
+        torch.nn.utils.clip_grad_norm_(ref_p, clip)
+    ref.step()
+
+    def closure():   # Lightning calls optimizer.step(closure=...) with the closure that runs backward
+        for q_, gr in zip(our_p2, grads):
+            q_.grad = gr.to(dev)
+        return torch.tensor(1.25)
+
+    assert float(ours2.step(closure)) == 1.25
+    for p_, q_ in zip(ref_p, our_p2):
+        assert rel(q_.data, p_.data) < 2e-6
 
 
 @pytest.mark.gpu
@@ -550,3 +646,54 @@ def test_force_matching_step_vs_oracle(g, dev):
     g.force_matching_backward(rep, head, d, lambda E_, F_: (E_ - E_t.to(E_)).pow(2).mean())
     far = max(rel(rp[k].grad, v.grad) for k, v in sd64.items() if v.grad is not None and k in rp)
     assert far > 0.05
+
+
+@pytest.mark.gpu
+def test_force_matching_with_attention_dropout(g, dev):
+    """Training mode, attn_dropout > 0 (the shipped yaml uses 0.1): every pass of force_matching_backward must run the
+    SAME stochastic network.  (i) With explicit masks the result matches the oracle's exact float64 double backward
+    with those masks; (ii) with self-drawn masks the step is reproduced bit-for-bit by replaying the recorded masks
+    (a fresh draw per stencil pass would put mask noise / 2h into the gradient)."""
+    p = 0.2
+    cfg = orc.OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, num_heads=4, sep_dir=True, sep_tensor=True,
+                           scale_edge=False)
+    z, pos, batch = blob([9, 12, 5], 22)
+    n_mol = 3
+    sd = orc.make_state_dict(cfg, seed=22)
+    sdh = orc.make_head_state_dict(cfg.n_atom_basis, seed=22)
+    gen = torch.Generator().manual_seed(6)
+    E_t = torch.randn(n_mol, 1, generator=gen)
+    F_t = torch.randn(z.numel(), 3, generator=gen) * 0.5
+
+    def loss_fn(E, F):
+        return (E - E_t.to(E)).pow(2).mean() + 10.0 * (F - F_t.to(F)).pow(2).mean()
+
+    rep = build(g, cfg, sd, dev, attn_dropout=p)
+    head = build_head(g, cfg, sdh, "silu", dev)
+    rep.train()
+    d = DataNS()
+    d.z, d.pos, d.batch, d.num_graphs = z.to(dev), pos.to(dev), batch.to(dev), n_mol
+    E_edges = orc.radius_graph(pos, batch, cfg.cutoff, cfg.max_num_neighbors).shape[1]
+    masks = [(torch.rand(E_edges, cfg.num_heads, generator=gen) >= p).float() / (1.0 - p)
+             for _ in range(cfg.n_interactions)]
+    sd64 = {k: v.double().requires_grad_(v.is_floating_point() and "radial_basis" not in k) for k, v in sd.items()}
+    sdh64 = {k: v.double().requires_grad_(k.startswith("out_net")) for k, v in sdh.items()}
+    Eo, Fo, _ = orc.energy_and_forces(sd64, sdh64, cfg, z, pos.double(), batch, n_mol, "silu",
+                                      drop_masks=[m.double() for m in masks])
+    loss_fn(Eo, Fo).backward()
+    loss, E, F = g.force_matching_backward(rep, head, d, loss_fn, attn_drop_masks=[m.to(dev) for m in masks])
+    assert rel(E, Eo.detach()) < TOL and rel(F, Fo.detach()) < TOL
+    rp = dict(rep.named_parameters())
+    worst = max(rel(rp[k].grad, v.grad) for k, v in sd64.items() if v.grad is not None and k in rp)
+    assert worst < 5e-3, worst
+    # (ii) self-drawn masks: recorded, shared by all passes, replayable
+    for q in list(rp.values()) + list(head.parameters()):
+        q.grad = None
+    g.force_matching_backward(rep, head, d, loss_fn)
+    used = rep.last_attn_drop_masks
+    assert used is not None and len(used) == cfg.n_interactions and used[0].shape == (E_edges, cfg.num_heads)
+    first = {k: v.grad.clone() for k, v in rp.items()}
+    for q in list(rp.values()) + list(head.parameters()):
+        q.grad = None
+    g.force_matching_backward(rep, head, d, loss_fn, attn_drop_masks=used)
+    assert all(torch.equal(first[k], rp[k].grad) for k in rp)
