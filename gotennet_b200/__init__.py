@@ -11,7 +11,8 @@ __version__ = "0.1.0"
 from ._lib import GotenError  # noqa: F401
 from .gotennet import EQFF, GATA, GotenNet, GotenNetWrapper  # noqa: F401
 from .layers import CosineCutoff, Dense, Distance, ExpNormalSmearing, MLP, TensorInit  # noqa: F401
-from .outputs import Atomwise, ScaleShift, SchnetMLP, shifted_softplus  # noqa: F401
+from .outputs import (Atomwise, Dipole, ElectronicSpatialExtentV2, GatedEquivariantBlock, ScaleShift,  # noqa: F401
+                      SchnetMLP, shifted_softplus)
 from .optim import FusedAdamW  # noqa: F401
 from .parallel import FlatGradBuffer, shard_bounds, take_shard  # noqa: F401
 from .data import MoleculeBatch, collate  # noqa: F401

@@ -19,6 +19,7 @@ _CTYPES = {
     "int64_t": ctypes.c_int64,
     "int32_t": ctypes.c_int32,
     "float": ctypes.c_float,
+    "double": ctypes.c_double,
     "void": None,
 }
 

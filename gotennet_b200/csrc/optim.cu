@@ -37,14 +37,14 @@ __global__ void __launch_bounds__(1024) sumsq_final_kernel(const float* __restri
 }
 
 struct AdamW {
-  float lr, beta1, beta2, eps, weight_decay, bias_c1, bias_c2_sqrt, max_norm, grad_scale;
+  float lr, beta1, beta2, omb1, omb2, eps, weight_decay, bias_c1, bias_c2_sqrt, max_norm, grad_scale;
 };
 
 // torch.optim.AdamW single-tensor update order: decay, lerp of the first moment, second moment, bias-corrected step
 __device__ __forceinline__ void adamw_one(float& p, float g, float& m, float& v, const AdamW& a) {
   p *= 1.0f - a.lr * a.weight_decay;
-  m = fmaf(g - m, 1.0f - a.beta1, m);
-  v = fmaf(1.0f - a.beta2, g * g, v * a.beta2);
+  m = fmaf(g - m, a.omb1, m);
+  v = fmaf(a.omb2, g * g, v * a.beta2);
   const float denom = sqrtf(v) / a.bias_c2_sqrt + a.eps;
   p -= (a.lr / a.bias_c1) * (m / denom);
 }
@@ -95,14 +95,16 @@ int goten_sumsq(const float* g, int64_t n, float* partial, float* out, void* str
 
 int goten_sumsq_workspace_floats(void) { return SUMSQ_BLOCKS; }
 
-int goten_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
-                     float weight_decay, float bias_c1, float bias_c2, float max_norm, const float* sumsq,
+int goten_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps,
+                     double weight_decay, float bias_c1, float bias_c2, float max_norm, const float* sumsq,
                      float grad_scale, void* stream) {
   if (n == 0) return 0;
   GOTEN_REQUIRE(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                   reinterpret_cast<uintptr_t>(v)) & 15) == 0, "goten_adamw_step needs 16-byte aligned buffers");
   GOTEN_REQUIRE(bias_c1 > 0.f && bias_c2 > 0.f, "bias corrections must be positive (step >= 1)");
-  AdamW a{lr, beta1, beta2, eps, weight_decay, bias_c1, sqrtf(bias_c2), max_norm, grad_scale};
+  // 1 - beta is formed in double like torch does on the host (float(1 - 0.999f) is 1.3e-5 off 1e-3)
+  AdamW a{(float)lr, (float)beta1, (float)beta2, (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, (float)weight_decay,
+          bias_c1, sqrtf(bias_c2), max_norm, grad_scale};
   int64_t grid = cdiv64(n >> 2, 256);
   if (grid > 148 * 8) grid = 148 * 8;
   if (grid < 1) grid = 1;

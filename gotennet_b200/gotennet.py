@@ -48,6 +48,28 @@ def _degree_ranges(lmax: int):
     return out
 
 
+def _resolve_targets(node):
+    """Instantiate Hydra-style `{_target_|__target__: path, **kwargs}` nodes of a checkpoint's hyper-parameters with the
+    class of the same NAME from this package (reference goten_model.py:118-124 lazy_instantiate + hydra.utils.instantiate);
+    unknown targets raise instead of importing arbitrary paths."""
+    if isinstance(node, Mapping):
+        d = {k: _resolve_targets(v) for k, v in node.items()}
+        target = d.pop("_target_", None)
+        target = d.pop("__target__", None) or target
+        if target is None:
+            return d
+        from . import layers as _layers
+        name = str(target).rsplit(".", 1)[-1]
+        known = {n: getattr(_layers, n) for n in ("CosineCutoff", "ExpNormalSmearing", "BesselBasis", "GaussianRBF")}
+        if name not in known:
+            raise ValueError(f"checkpoint hyper-parameter target {target!r} has no counterpart in gotennet_b200 "
+                             f"(known: {sorted(known)})")
+        return known[name](**d)
+    if isinstance(node, (list, tuple)):
+        return type(node)(_resolve_targets(v) for v in node)
+    return node
+
+
 _ALLOWED_UPDATE_PARTS = ["gated", "gatedt", "norej", "norm", "mlp", "mlpa", "act", "linw", "linwa", "ln", "postln"]
 
 
@@ -310,18 +332,24 @@ class GotenNet(nn.Module):
 
     @classmethod
     def load_from_checkpoint(cls, checkpoint_path: str, device="cpu"):
-        """Lightning checkpoint -> module (reference gotennet.py:904-946, with its missing `import os` fixed)."""
+        """Lightning checkpoint of a reference `GotenModel` -> representation module (reference gotennet.py:904-946 with
+        its missing `import os` fixed; checkpoints come from goten_model.py:160-168 / Lightning's ModelCheckpoint).
+
+        `hyper_parameters["representation"]` is the Hydra node of configs/model/gotennet.yaml:18-40 as Lightning saved
+        it: a mapping (dict or OmegaConf DictConfig) that may still carry `_target_` / `__target__` entries, also nested
+        (`cutoff_fn: {__target__: ...CosineCutoff, cutoff: 5.0}`).  The top-level target is dropped (`cls` decides), nested
+        ones are instantiated from this package's classes of the same name - never imported by path.  `state_dict` keys
+        lose their `representation.` prefix; `output_modules.*` (the task heads) are skipped; loading is strict."""
         if not os.path.exists(checkpoint_path):
             raise FileNotFoundError(f"Checkpoint file {checkpoint_path} does not exist.")
-        ckpt = torch.load(checkpoint_path, map_location=device)
+        ckpt = torch.load(checkpoint_path, map_location=device, weights_only=False)
         if "representation" in ckpt:
             ckpt = ckpt["representation"]
         assert "hyper_parameters" in ckpt, "Checkpoint must contain 'hyper_parameters' key."
         hp = ckpt["hyper_parameters"]
         assert "representation" in hp, "Hyperparameters must contain 'representation' key."
-        rep_cfg = dict(hp["representation"])
-        rep_cfg.pop("_target_", None)
-        rep_cfg.pop("__target__", None)
+        rep_cfg = {k: _resolve_targets(v) for k, v in dict(hp["representation"]).items()
+                   if k not in ("_target_", "__target__")}
         assert "state_dict" in ckpt, "Checkpoint must contain 'state_dict' key."
         sd = {}
         for k, v in ckpt["state_dict"].items():

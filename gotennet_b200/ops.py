@@ -801,3 +801,159 @@ class AtomwiseReduceFn(torch.autograd.Function):
                    _ptr(g_yi.contiguous() if g_yi is not None else None), _ptr(stddev), ctx.n_stat, _ptr(mol_ptr), N,
                    ctx.n_mol, n_out, ctx.mode, _ptr(g_raw), _stream())
         return g_raw, None, None, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------
+# equivariant read-out heads (reference models/components/outputs.py:24-104, :379-542)
+# ---------------------------------------------------------------------------
+def _act_apply(kind, z):
+    if kind == ACT_NONE:
+        return z
+    y = torch.empty_like(z)
+    lib().call("goten_act_fwd", kind, _ptr(z), z.numel(), _ptr(y), _stream())
+    return y
+
+
+class GatedEquivariantFn(torch.autograd.Function):
+    """GatedEquivariantBlock.forward (outputs.py:76-103): scalars [N,ns], vectors [N,3,nvin] ->
+    (s_out [N,nso], v_out [N,3,nv]).  Three GEMMs (mix_vectors, scalar_net.0 with its activation, scalar_net.1) around
+    two element-wise kernels (vector norms into the context, gating)."""
+
+    @staticmethod
+    def forward(ctx, scalars, vectors, Wmix, W1, b1, W2, b2, nso, nv, act, sact):
+        _chk(scalars, vectors, Wmix, W1, b1, W2, b2)
+        scalars, vectors = _f32(scalars.contiguous()), _f32(vectors.contiguous())
+        N, ns = scalars.shape
+        nvin = vectors.shape[2]
+        if vectors.shape[:2] != (N, 3) or Wmix.shape != (2 * nv, nvin) or W2.shape[0] != nso + nv:
+            raise GotenError("GatedEquivariantBlock: inconsistent shapes")
+        dev = scalars.device
+        L_, st = lib(), _stream()
+        vmix = torch.empty(N, 3, 2 * nv, device=dev)
+        if N > 0:
+            gemm(vectors, nvin, 0, Wmix, nvin, 1, vmix, 2 * nv, 3 * N, 2 * nv, nvin)
+        cx = torch.empty(N, ns + nv, device=dev)
+        L_.call("goten_geb_ctx_fwd", _ptr(scalars), _ptr(vmix), N, ns, nv, _ptr(cx), st)
+        if act == ACT_SILU:
+            Z1, A1 = linear_fwd(cx, W1, b1, act=True)
+        else:
+            Z1 = linear_fwd(cx, W1, b1)
+            A1 = _act_apply(act, Z1)
+        x = linear_fwd(A1, W2, b2)
+        s_out = torch.empty(N, nso, device=dev)
+        v_out = torch.empty(N, 3, nv, device=dev)
+        L_.call("goten_geb_gate_fwd", _ptr(x), _ptr(vmix), N, nso, nv, sact, _ptr(s_out), _ptr(v_out), st)
+        ctx.dims = (N, ns, nvin, nso, nv, act, sact)
+        ctx.save_for_backward(vectors, Wmix, W1, W2, vmix, cx, Z1, A1, x)
+        return s_out, v_out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_s, g_v):
+        vectors, Wmix, W1, W2, vmix, cx, Z1, A1, x = ctx.saved_tensors
+        N, ns, nvin, nso, nv, act, sact = ctx.dims
+        dev = x.device
+        L_, st = lib(), _stream()
+        g_s = g_s.contiguous() if g_s is not None else None
+        g_v = g_v.contiguous() if g_v is not None else None
+        g_x = torch.empty_like(x)
+        g_vmix = torch.empty_like(vmix)
+        L_.call("goten_geb_gate_bwd", _ptr(g_s), _ptr(g_v), _ptr(x), _ptr(vmix), N, nso, nv, sact, _ptr(g_x), _ptr(g_vmix),
+                st)
+        g_A1, dW2, db2 = linear_bwd(g_x, A1, W2)
+        if act != ACT_NONE:
+            g_Z1 = torch.empty_like(g_A1)
+            L_.call("goten_act_bwd", act, _ptr(g_A1), _ptr(Z1), g_A1.numel(), _ptr(g_Z1), st)
+        else:
+            g_Z1 = g_A1
+        g_cx, dW1, db1 = linear_bwd(g_Z1, cx, W1)
+        g_sc = torch.empty(N, ns, device=dev)
+        L_.call("goten_geb_ctx_bwd", _ptr(g_cx), _ptr(vmix), N, ns, nv, _ptr(g_sc), _ptr(g_vmix), st)
+        g_vec = torch.empty_like(vectors)
+        dWmix = torch.empty_like(Wmix)
+        if N > 0:
+            gemm(g_vmix, 2 * nv, 0, Wmix, nvin, 0, g_vec, nvin, 3 * N, nvin, 2 * nv)
+            gemm(g_vmix, 2 * nv, 1, vectors, nvin, 0, dWmix, nvin, 2 * nv, nvin, 3 * N)
+        else:
+            dWmix.zero_()
+        return g_sc, g_vec, dWmix, dW1, db1, dW2, db2, None, None, None, None
+
+
+class DipoleAtomFn(torch.autograd.Function):
+    """yi [N,3] = atomic dipoles + pos * charges, charges = stddev * q + mean when standardised (outputs.py:446-453)."""
+
+    @staticmethod
+    def forward(ctx, l1, l0, pos, sd, mu):
+        _chk(l1, l0, pos)
+        l1, l0, pos = _f32(l1.contiguous()), _f32(l0.contiguous()), _f32(pos.contiguous())
+        N = l0.numel()
+        yi = torch.empty(N, 3, device=l1.device)
+        lib().call("goten_dipole_atom_fwd", _ptr(l1), _ptr(l0), _ptr(pos), float(sd), float(mu), N, _ptr(yi), _stream())
+        ctx.stats = (float(sd), float(mu))
+        ctx.save_for_backward(l0, pos)
+        return yi
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        l0, pos = ctx.saved_tensors
+        sd, mu = ctx.stats
+        N = l0.numel()
+        g = g.contiguous()
+        g_l1 = torch.empty(N, 3, device=g.device)
+        g_l0 = torch.empty_like(l0)
+        g_pos = torch.empty(N, 3, device=g.device) if ctx.needs_input_grad[2] else None
+        lib().call("goten_dipole_atom_bwd", _ptr(g), _ptr(l0), _ptr(pos), sd, mu, N, _ptr(g_l1), _ptr(g_l0), _ptr(g_pos),
+                   _stream())
+        return g_l1, g_l0, g_pos, None, None
+
+
+class RowNormFn(torch.autograd.Function):
+    """||v[m,:]||_2 with keepdim (predict_magnitude, outputs.py:460-461)."""
+
+    @staticmethod
+    def forward(ctx, v):
+        _chk(v)
+        v = _f32(v.contiguous())
+        M, D = v.shape
+        y = torch.empty(M, 1, device=v.device)
+        lib().call("goten_rownorm_fwd", _ptr(v), M, D, _ptr(y), _stream())
+        ctx.save_for_backward(v)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (v,) = ctx.saved_tensors
+        g_v = torch.empty_like(v)
+        lib().call("goten_rownorm_bwd", _ptr(g.contiguous()), _ptr(v), v.shape[0], v.shape[1], _ptr(g_v), _stream())
+        return g_v
+
+
+class SpatialExtentFn(torch.autograd.Function):
+    """ElectronicSpatialExtentV2.forward (outputs.py:522-541): x [N,1], pos, z, mass table -> y [n_mol,1]."""
+
+    @staticmethod
+    def forward(ctx, x, pos, z, mass, mol_ptr, n_mol):
+        _chk(x, pos, z, mass, mol_ptr)
+        x, pos = _f32(x.contiguous()), _f32(pos.contiguous())
+        N = x.shape[0]
+        dev = x.device
+        yi = torch.empty(N, 1, device=dev)
+        y = torch.zeros(n_mol, 1, device=dev)
+        cen = torch.zeros(max(n_mol, 1), 4, device=dev)
+        lib().call("goten_ese_fwd", _ptr(x), _ptr(pos), _ptr(z), _ptr(mass), mass.numel(), _ptr(mol_ptr), n_mol, _ptr(yi),
+                   _ptr(y), _ptr(cen), _stream())
+        ctx.n_mol = n_mol
+        ctx.save_for_backward(x, pos, z, mass, mol_ptr, cen)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        x, pos, z, mass, mol_ptr, cen = ctx.saved_tensors
+        g_x = torch.empty_like(x)
+        g_pos = torch.empty_like(pos) if ctx.needs_input_grad[1] else None
+        lib().call("goten_ese_bwd", _ptr(g.contiguous()), _ptr(x), _ptr(pos), _ptr(z), _ptr(mass), mass.numel(),
+                   _ptr(mol_ptr), ctx.n_mol, _ptr(cen), _ptr(g_x), _ptr(g_pos), _stream())
+        return g_x, g_pos, None, None, None, None

@@ -9,8 +9,10 @@ the tcgen05 / SIMT GEMM kernels (SiLU fused in the epilogue), standardisation + 
 the per-molecule sum is one deterministic segmented-reduction kernel (the reference scatters
 with atomics), and forces come from the hand-written backward of the interaction block.
 
-Not implemented (raises): equivariant out-nets (`GatedEquivariantBlock` heads used by Dipole /
-ElectronicSpatialExtentV2), and second-order autograd through the block -- `create_graph=True`
+`GatedEquivariantBlock`, `Dipole` and `ElectronicSpatialExtentV2` (the remaining QM9 heads, SURVEY §8 f4,
+reference outputs.py:24-104, :379-542) follow at the bottom of the file on the same kernels.
+
+Not implemented (raises): custom out-nets passed to Atomwise, and second-order autograd through the block -- `create_graph=True`
 (the reference default, outputs.py:248) still yields correct first-order forces, but
 back-propagating *through* them (force-loss training) raises instead of silently dropping terms.
 """
@@ -183,3 +185,106 @@ class Atomwise(nn.Module):
                 dy = _FirstOrderOnly.apply(dy, inputs.pos, self.derivative)
             result[self.derivative] = dy
         return result
+
+
+def _n_mol_of(inputs) -> int:
+    n_mol = getattr(inputs, "num_graphs", None)
+    if n_mol is None:  # same host read torch_scatter does to size its output
+        n_mol = int(inputs.batch[-1].item()) + 1 if inputs.batch.numel() else 0
+    return int(n_mol)
+
+
+class GatedEquivariantBlock(nn.Module):
+    """Invariant + equivariant feature mixing for tensorial read-outs (reference outputs.py:24-104); same constructor,
+    attributes and state_dict keys (`mix_vectors.weight`, `scalar_net.{0,1}.{weight,bias}`)."""
+
+    def __init__(self, n_sin: int, n_vin: int, n_sout: int, n_vout: int, n_hidden: int, activation=F.silu,
+                 sactivation=None):
+        super().__init__()
+        self.n_sin, self.n_vin, self.n_sout, self.n_vout, self.n_hidden = n_sin, n_vin, n_sout, n_vout, n_hidden
+        self.mix_vectors = Dense(n_vin, 2 * n_vout, activation=None, bias=False)
+        self.scalar_net = nn.Sequential(Dense(n_sin + n_vout, n_hidden, activation=activation),
+                                        Dense(n_hidden, n_sout + n_vout, activation=None))
+        self.sactivation = sactivation
+
+    def forward(self, scalars: torch.Tensor, vectors: torch.Tensor):
+        """scalars [N, n_sin], vectors [N, 3, n_vin] -> (s_out [N, n_sout], v_out [N, 3, n_vout])."""
+        with ops.device_of(scalars):
+            d0, d1 = self.scalar_net[0], self.scalar_net[1]
+            return ops.GatedEquivariantFn.apply(scalars, vectors, self.mix_vectors.weight, d0.weight, d0.bias, d1.weight,
+                                                d1.bias, self.n_sout, self.n_vout, _act_kind(d0.activation),
+                                                _act_kind(self.sactivation))
+
+
+class Dipole(nn.Module):
+    """Dipole-moment read-out (reference outputs.py:379-468): two gated equivariant blocks on (h, X[:, :3]) -> latent
+    atomic charges and dipoles; mu = sum_atoms (mu_atom + q_atom * pos); optional magnitude.  Same constructor, result
+    keys (`property`, `property + "_vector"`) and state_dict keys (`equivariant_layers.{0,1}.*`)."""
+
+    def __init__(self, n_in: int, n_hidden: Optional[int] = None, activation=F.silu, property: str = "dipole",
+                 predict_magnitude: bool = False, output_v: bool = True, mean: Optional[torch.Tensor] = None,
+                 stddev: Optional[torch.Tensor] = None):
+        super().__init__()
+        self.stddev, self.mean, self.output_v = stddev, mean, output_v
+        if n_hidden is None:
+            n_hidden = n_in
+        if type(activation) is str:
+            activation = str2act(activation)
+        self.property, self.derivative, self.predict_magnitude = property, None, predict_magnitude
+        self.equivariant_layers = nn.ModuleList([
+            GatedEquivariantBlock(n_sin=n_in, n_vin=n_in, n_sout=n_hidden, n_vout=n_hidden, n_hidden=n_hidden,
+                                  activation=activation, sactivation=activation),
+            GatedEquivariantBlock(n_sin=n_hidden, n_vin=n_hidden, n_sout=1, n_vout=1, n_hidden=n_hidden,
+                                  activation=activation)])
+        self.requires_dr = False
+        self.requires_stress = False
+        self.aggregation_mode = "sum"
+
+    def forward(self, inputs):
+        with ops.device_of(inputs.pos):
+            l0 = inputs.representation
+            l1 = inputs.vector_representation[:, :3, :]
+            for eqlayer in self.equivariant_layers:
+                l0, l1 = eqlayer(l0, l1)
+            standardised = self.stddev is not None
+            sd = float(self.stddev) if standardised else 1.0
+            mu = float(self.mean) if standardised and self.mean is not None else 0.0
+            n_mol = _n_mol_of(inputs)
+            mol_ptr = ops.mol_ptr_from_batch(inputs.batch, n_mol)
+            yi = ops.DipoleAtomFn.apply(l1.reshape(-1, 3), l0.reshape(-1), inputs.pos, sd, mu)
+            _, y = ops.AtomwiseReduceFn.apply(yi, None, None, None, None, mol_ptr, n_mol, 1)
+            result = {}
+            if self.output_v:
+                _, yv = ops.AtomwiseReduceFn.apply(l1.reshape(-1, 3), None, None, None, None, mol_ptr, n_mol, 1)
+                result[self.property + "_vector"] = yv.unsqueeze(-1)
+            if self.predict_magnitude:
+                y = ops.RowNormFn.apply(y)
+            result[self.property] = y
+            return result
+
+
+class ElectronicSpatialExtentV2(Atomwise):
+    """<r^2> read-out (reference outputs.py:471-542): per-atom scalar from the Atomwise MLP weighted by the squared
+    distance to the molecule's centre of mass, summed per molecule.  `atomic_mass` is a buffer as in the reference."""
+
+    def __init__(self, n_in: int, n_layers: int = 2, n_hidden: Optional[int] = None, activation=shifted_softplus,
+                 property: str = "y", contributions: Optional[str] = None, mean: Optional[torch.Tensor] = None,
+                 stddev: Optional[torch.Tensor] = None, outnet: Optional[nn.Module] = None):
+        super().__init__(n_in, 1, "sum", n_layers, n_hidden, activation=activation, mean=mean, stddev=stddev,
+                         outnet=outnet, property=property, contributions=contributions)
+        from .atomic_data import ATOMIC_MASSES
+        self.register_buffer("atomic_mass", torch.tensor(ATOMIC_MASSES, dtype=torch.float32))
+
+    def forward(self, inputs):
+        with ops.device_of(inputs.pos):
+            x = self.out_net(inputs)
+            if not x.is_cuda:
+                raise GotenError("gotennet_b200 kernels need CUDA tensors (there is no CPU path)")
+            n_mol = _n_mol_of(inputs)
+            mol_ptr = ops.mol_ptr_from_batch(inputs.batch, n_mol)
+            y = ops.SpatialExtentFn.apply(x, inputs.pos, inputs.z.contiguous().long(), self.atomic_mass.float(), mol_ptr,
+                                          n_mol)
+            result = {self.property: y}
+            if self.contributions:
+                result[self.contributions] = x
+            return result

@@ -309,6 +309,34 @@ int goten_atomwise_reduce_bwd(const float* g_y, const float* g_yi, const float* 
 int goten_act_fwd(int kind, const float* x, int64_t n, float* y, void* stream);
 int goten_act_bwd(int kind, const float* g, const float* x, int64_t n, float* out, void* stream);
 
+/* ------------------------------- equivariant read-out heads --
+ * Element-wise / per-molecule stages of GatedEquivariantBlock (models/components/outputs.py:24-104: vmix [N][3][2*nv]
+ * = mix_vectors(vectors) = [V | W]; ctx = [scalars | ||V||]; x = scalar_net(ctx) [N][nso+nv]; s_out = sact(x[:, :nso]),
+ * v_out = x[:, nso:] * W), of Dipole (outputs.py:437-467: yi = mu_atom + pos * (stddev * q + mean), per-molecule sum
+ * through goten_atomwise_reduce_*, optional magnitude = row norm) and of ElectronicSpatialExtentV2
+ * (outputs.py:522-541: mass-weighted centroid per molecule, yi = |pos - c|^2 * x, y = per-molecule sum; `centroid`
+ * [n_mol][4] keeps (c, total mass) for the backward).  sact: 0 none, 1 SiLU, 2 shifted softplus.  The dense layers of
+ * the blocks are goten_gemm_scaled calls.  Norm gradients at a zero vector are 0 (torch semantics).               */
+int goten_geb_ctx_fwd(const float* scalars, const float* vmix, int64_t n_nodes, int ns, int nv, float* ctx,
+                      void* stream);
+int goten_geb_ctx_bwd(const float* g_ctx, const float* vmix, int64_t n_nodes, int ns, int nv, float* g_scalars,
+                      float* g_vmix, void* stream);
+int goten_geb_gate_fwd(const float* x, const float* vmix, int64_t n_nodes, int nso, int nv, int sact, float* s_out,
+                       float* v_out, void* stream);
+int goten_geb_gate_bwd(const float* g_s, const float* g_v, const float* x, const float* vmix, int64_t n_nodes,
+                       int nso, int nv, int sact, float* g_x, float* g_vmix, void* stream);
+int goten_dipole_atom_fwd(const float* l1, const float* l0, const float* pos, float stddev, float mean,
+                          int64_t n_nodes, float* yi, void* stream);
+int goten_dipole_atom_bwd(const float* g_yi, const float* l0, const float* pos, float stddev, float mean,
+                          int64_t n_nodes, float* g_l1, float* g_l0, float* g_pos, void* stream);
+int goten_rownorm_fwd(const float* v, int64_t rows, int dim, float* y, void* stream);
+int goten_rownorm_bwd(const float* g, const float* v, int64_t rows, int dim, float* g_v, void* stream);
+int goten_ese_fwd(const float* x, const float* pos, const int64_t* z, const float* mass, int mass_rows,
+                  const int32_t* mol_ptr, int n_mol, float* yi, float* y, float* centroid, void* stream);
+int goten_ese_bwd(const float* g_y, const float* x, const float* pos, const int64_t* z, const float* mass,
+                  int mass_rows, const int32_t* mol_ptr, int n_mol, const float* centroid, float* g_x,
+                  float* g_pos, void* stream);
+
 /* --------------------------------------------------------------- optimiser --
  * Training step of the reference on one FLAT fp32 parameter buffer
  * (models/goten_model.py:521-578: torch.optim.AdamW(eps=1e-7), weight decay on every
@@ -321,8 +349,8 @@ int goten_act_bwd(int kind, const float* g, const float* x, int64_t n, float* ou
  *   The clip coefficient is formed on the device: no host read between backward and step. */
 int goten_sumsq(const float* g, int64_t n, float* partial, float* out, void* stream);
 int goten_sumsq_workspace_floats(void);
-int goten_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1,
-                     float beta2, float eps, float weight_decay, float bias_c1, float bias_c2,
+int goten_adamw_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                     double beta2, double eps, double weight_decay, float bias_c1, float bias_c2,
                      float max_norm, const float* sumsq, float grad_scale, void* stream);
 
 #ifdef __cplusplus

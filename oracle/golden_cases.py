@@ -80,6 +80,18 @@ HEAD_CASES = {
 }
 
 
+# remaining QM9 heads: Dipole (two gated equivariant blocks, magnitude output, standardised charges as the
+# QM9 task builds it, QM9Task.py:172-179) and ElectronicSpatialExtentV2 (QM9Task.py:181-185)
+HEAD2_CASES = {
+    "dipole_l2": dict(kind="dipole", cfg=OracleConfig(n_atom_basis=64, n_interactions=2, lmax=2, sep_dir=True,
+                                                      sep_tensor=True, scale_edge=False), atoms=[14, 1, 9, 20], seed=31,
+                      mean=0.3, stddev=1.7, predict_magnitude=True),
+    "dipole_vec_l1": dict(kind="dipole", cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=1, num_heads=4),
+                          atoms=[11, 6], seed=32, mean=None, stddev=None, predict_magnitude=False),
+    "ese_l2": dict(kind="ese", cfg=OracleConfig(n_atom_basis=64, n_interactions=2, lmax=2, sep_dir=True, sep_tensor=True,
+                                                scale_edge=False), atoms=[16, 2, 12], seed=33),
+}
+
 def blob(n_atoms, seed, sigma0=1.45):
     """Gaussian-blob molecules of the given sizes: z [N] i64, pos [N,3] f32, batch [N] i64."""
     g = torch.Generator().manual_seed(seed)
@@ -102,3 +114,20 @@ def grad_fingerprint(g):
     if g.dim() == 1:
         return g
     return g @ probe_vector(g.shape[1]).to(g.dtype).to(g.device)
+
+
+def head2_loss(kind, y, yv, n_mol):
+    """Probe loss of the HEAD2 cases: seeded weights on the head output (+ the vector output for Dipole)."""
+    w = probe_vector(n_mol * y.shape[1]).view(n_mol, y.shape[1]).to(y)
+    loss = (y * w).sum()
+    if kind == "dipole":
+        loss = loss + 0.5 * (yv.squeeze(-1) * probe_vector(n_mol * 3 + 1)[:n_mol * 3].view(n_mol, 3).to(y)).sum()
+    return loss
+
+
+def head2_state(spec):
+    from . import gotennet_oracle as orc
+    C = spec["cfg"].n_atom_basis
+    if spec["kind"] == "dipole":
+        return orc.make_dipole_state_dict(C, seed=spec["seed"])
+    return orc.make_head_state_dict(C, seed=spec["seed"], atomref=False)

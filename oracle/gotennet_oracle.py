@@ -551,6 +551,86 @@ def energy_and_forces(sd, sd_head, cfg: OracleConfig, z, pos, batch, n_mol: int,
     return y, -dy, h
 
 
+# --------------------------------------------------------------------------
+# equivariant read-out heads (components/outputs.py:24-104, :379-542)
+# --------------------------------------------------------------------------
+def _head_act(name: Optional[str], x: Tensor) -> Tensor:
+    if name is None:
+        return x
+    return F.silu(x) if name == "silu" else F.softplus(x) - math.log(2.0)
+
+
+def gated_equivariant_block(sd, prefix: str, scalars: Tensor, vectors: Tensor, n_sout: int, n_vout: int,
+                            activation: str = "silu", sactivation: Optional[str] = None):
+    """GatedEquivariantBlock.forward (outputs.py:76-103): scalars [N,n_sin], vectors [N,3,n_vin]."""
+    vmix = F.linear(vectors, sd[prefix + "mix_vectors.weight"])                     # :89 (no bias)
+    V, W = torch.split(vmix, n_vout, dim=-1)                                        # :90
+    Vn = torch.norm(V, dim=-2)                                                      # :91
+    ctx = torch.cat([scalars, Vn], dim=-1)                                          # :93
+    x = _head_act(activation, F.linear(ctx, sd[prefix + "scalar_net.0.weight"], sd[prefix + "scalar_net.0.bias"]))
+    x = F.linear(x, sd[prefix + "scalar_net.1.weight"], sd[prefix + "scalar_net.1.bias"])   # :94
+    s_out, g = torch.split(x, [n_sout, n_vout], dim=-1)                             # :95
+    v_out = g.unsqueeze(-2) * W                                                     # :96
+    return _head_act(sactivation, s_out), v_out                                     # :98-101
+
+
+def make_dipole_state_dict(n_in: int, n_hidden: Optional[int] = None, seed: int = 0, dtype=torch.float32):
+    """Deterministic weights under the reference's Dipole key names (`equivariant_layers.{0,1}.*`, outputs.py:420-427)."""
+    g = torch.Generator().manual_seed(20_000 + seed)
+    nh = n_in if n_hidden is None else n_hidden
+    sd: Dict[str, Tensor] = {}
+
+    def lin(key, n_out, n_inp, bias=True):
+        bound = math.sqrt(6.0 / (n_out + n_inp))
+        sd[key + ".weight"] = ((torch.rand(n_out, n_inp, generator=g, dtype=torch.float64) * 2 - 1) * bound).to(dtype)
+        if bias:
+            sd[key + ".bias"] = ((torch.rand(n_out, generator=g, dtype=torch.float64) * 2 - 1) * 0.1).to(dtype)
+
+    for i, (sin, vin, sout, vout) in enumerate([(n_in, n_in, nh, nh), (nh, nh, 1, 1)]):
+        p = f"equivariant_layers.{i}."
+        lin(p + "mix_vectors", 2 * vout, vin, bias=False)
+        lin(p + "scalar_net.0", nh, sin + vout)
+        lin(p + "scalar_net.1", sout + vout, nh)
+    return sd
+
+
+def dipole_forward(sd, h: Tensor, X: Tensor, pos: Tensor, batch: Tensor, n_mol: int, n_hidden: Optional[int] = None,
+                   mean=None, stddev=None, predict_magnitude: bool = False, activation: str = "silu"):
+    """Dipole.forward (outputs.py:437-467).  Returns (y [n_mol,3] or its magnitude [n_mol,1], y_vector [n_mol,3,1])."""
+    nh = h.shape[1] if n_hidden is None else n_hidden
+    l0, l1 = h, X[:, :3, :]                                                         # :449-450
+    l0, l1 = gated_equivariant_block(sd, "equivariant_layers.0.", l0, l1, nh, nh, activation, activation)
+    l0, l1 = gated_equivariant_block(sd, "equivariant_layers.1.", l0, l1, 1, 1, activation, None)
+    if stddev is not None:
+        l0 = stddev * l0 + mean                                                     # :456-457
+    y = torch.squeeze(l1, -1) + pos * l0                                            # :459-463
+    y = torch.zeros(n_mol, 3, dtype=y.dtype).index_add_(0, batch, y)                # :465
+    yv = torch.zeros(n_mol, 3, 1, dtype=l1.dtype).index_add_(0, batch, l1)          # :467
+    if predict_magnitude:
+        y = torch.norm(y, dim=1, keepdim=True)                                      # :470-471
+    return y, yv
+
+
+def spatial_extent_forward(sd_head, h: Tensor, z: Tensor, pos: Tensor, batch: Tensor, n_mol: int, masses: Tensor,
+                           activation: str = "ssp"):
+    """ElectronicSpatialExtentV2.forward (outputs.py:522-541): the Atomwise MLP alone (no ScaleShift / atomref),
+    weighted by the squared distance to the centre of mass.  Returns (y [n_mol,1], x [N,1])."""
+    sd_mlp = {k: v for k, v in sd_head.items() if k.startswith("out_net")}
+    x = h
+    n_lin = len([k for k in sd_mlp if k.endswith(".weight")])
+    for i in range(n_lin):
+        x = F.linear(x, sd_mlp[f"out_net.1.out_net.{i}.weight"], sd_mlp[f"out_net.1.out_net.{i}.bias"])
+        if i < n_lin - 1:
+            x = _head_act(activation, x)
+    mass = masses.to(pos.dtype)[z].view(-1, 1)                                      # :525
+    num = torch.zeros(n_mol, 3, dtype=pos.dtype).index_add_(0, batch, mass * pos)
+    den = torch.zeros(n_mol, 1, dtype=pos.dtype).index_add_(0, batch, mass)
+    c = num / den                                                                   # :526
+    yi = torch.norm(pos - c[batch], dim=1, keepdim=True) ** 2 * x                   # :528-529
+    y = torch.zeros(n_mol, 1, dtype=yi.dtype).index_add_(0, batch, yi)              # :531
+    return y, x
+
+
 def synth_batch(kind: str, n_mol: int, seed: int = 0):
     """Deterministic synthetic batches: returns z [N] int64, pos [N,3] f32, batch [N] int64."""
     g = torch.Generator().manual_seed(seed)

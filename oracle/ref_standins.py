@@ -234,7 +234,6 @@ def install() -> None:
     sys.modules["omegaconf"] = oc
 
     # read-out heads (models/components/outputs.py:3,6): torch_scatter.scatter and an `ase` placeholder
-    # (ase.data.atomic_masses is only touched by ElectronicSpatialExtentV2, outputs.py:513 -- not on our path)
     ts = types.ModuleType("torch_scatter")
     ts.scatter = lambda src, index, dim=0, out=None, dim_size=None, reduce="sum": _scatter(
         src, index, dim=dim, dim_size=dim_size, reduce=reduce)
@@ -243,7 +242,11 @@ def install() -> None:
     ase_data = types.ModuleType("ase.data")
     import numpy as _np
 
-    ase_data.atomic_masses = _np.zeros(119)
+    # ASE itself is absent offline: the table the product ships (IUPAC 2016, gotennet_b200/atomic_data.py) stands in
+    # for ase.data.atomic_masses, so the reference's ElectronicSpatialExtentV2 (outputs.py:513) runs verbatim
+    from gotennet_b200.atomic_data import ATOMIC_MASSES as _MASSES
+
+    ase_data.atomic_masses = _np.asarray(_MASSES, dtype=_np.float64)
     ase.data = ase_data
     sys.modules["ase"] = ase
     sys.modules["ase.data"] = ase_data

@@ -697,3 +697,56 @@ def test_force_matching_with_attention_dropout(g, dev):
         q.grad = None
     g.force_matching_backward(rep, head, d, loss_fn, attn_drop_masks=used)
     assert all(torch.equal(first[k], rp[k].grad) for k in rp)
+
+
+# ------------------------------- remaining QM9 heads -----------
+from oracle.golden_cases import HEAD2_CASES, head2_loss, head2_state  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(HEAD2_CASES))
+def test_dipole_and_spatial_extent_heads_golden(g, dev, name, golden_dir):
+    """GotenNetWrapper + Dipole / ElectronicSpatialExtentV2 on the CUDA path against the verbatim reference's golden
+    vectors (reference outputs.py:379-542): outputs, d/dpos and every head / representation parameter gradient."""
+    spec = HEAD2_CASES[name]
+    cfg, kind = spec["cfg"], spec["kind"]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    n_mol = len(spec["atoms"])
+    C = cfg.n_atom_basis
+    rep = build(g, cfg, orc.make_state_dict(cfg, seed=spec["seed"]), dev)
+    sdh = head2_state(spec)
+    if kind == "dipole":
+        head = g.Dipole(n_in=C, predict_magnitude=spec["predict_magnitude"], property="property",
+                        mean=None if spec["mean"] is None else torch.tensor(spec["mean"]),
+                        stddev=None if spec["stddev"] is None else torch.tensor(spec["stddev"]))
+        head.load_state_dict(sdh, strict=True)
+    else:
+        head = g.ElectronicSpatialExtentV2(n_in=C, property="property", contributions="contrib")
+        missing = head.load_state_dict(sdh, strict=False)
+        assert missing.missing_keys == ["atomic_mass"] and not missing.unexpected_keys
+    head = head.to(dev)
+    d = DataNS()
+    d.z, d.pos, d.batch = z.to(dev), pos.to(dev).requires_grad_(True), batch.to(dev)
+    d.representation, d.vector_representation = rep(d)
+    res = head(d)
+    assert rel(res["property"].detach(), gold["y"]) < TOL
+    if kind == "dipole":
+        assert res["property_vector"].shape == (n_mol, 3, 1)
+        assert rel(res["property_vector"].detach(), gold["y_vector"]) < TOL
+    else:
+        assert rel(res["contrib"].detach(), gold["contrib"]) < TOL
+    head2_loss(kind, res["property"], res.get("property_vector"), n_mol).backward()
+    assert rel(d.pos.grad, gold["grad_pos"]) < TOL
+    hp, rp = dict(head.named_parameters()), dict(rep.named_parameters())
+    n = 0
+    for k in gold.files:
+        if k.startswith("gradh_"):
+            assert rel(grad_fingerprint(hp[k[6:]].grad.cpu()), gold[k]) < TOL, k
+            n += 1
+        elif k.startswith("grad_") and k != "grad_pos":
+            p = rp[k[5:]]
+            gr = p.grad if p.grad is not None else torch.zeros_like(p)
+            assert rel(grad_fingerprint(gr.cpu()), gold[k]) < TOL, k
+            n += 1
+    assert n == len(hp) + len(orc.state_dict_spec(cfg))

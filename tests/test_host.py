@@ -58,6 +58,16 @@ def test_state_dict_matches_reference_module(g):
         b = g.GotenNetWrapper(cutoff_fn=g.CosineCutoff(5.0), **kw).state_dict()
         assert set(a) == set(b)
         assert all(a[k].shape == b[k].shape for k in a)
+    # read-out heads: identical state_dict layouts and result keys
+    from gotennet.models.components import outputs as ro
+    for mk_ref, mk_ours in ((lambda: ro.Atomwise(n_in=32, atomref=torch.zeros(100, 1)),
+                             lambda: g.Atomwise(n_in=32, atomref=torch.zeros(100, 1))),
+                            (lambda: ro.Dipole(n_in=32, predict_magnitude=True), lambda: g.Dipole(n_in=32, predict_magnitude=True)),
+                            (lambda: ro.Dipole(n_in=32, n_hidden=24), lambda: g.Dipole(n_in=32, n_hidden=24)),
+                            (lambda: ro.ElectronicSpatialExtentV2(n_in=32), lambda: g.ElectronicSpatialExtentV2(n_in=32))):
+        a, b = mk_ref().state_dict(), mk_ours().state_dict()
+        assert set(a) == set(b), set(a) ^ set(b)
+        assert all(a[k].shape == b[k].shape for k in a)
 
 
 def test_constructor_errors(g):
@@ -205,3 +215,79 @@ def test_force_matching_algorithm_on_a_torch_model(g):
             p.grad = None
     with pytest.raises(ValueError):
         g.force_matching_backward(rep, head, d, loss_fn, order=3)
+
+
+YAML_REPRESENTATION = {  # reference configs/model/gotennet.yaml:18-40 as Lightning stores it in hyper_parameters
+    "__target__": "gotennet.models.representation.gotennet.GotenNetWrapper",
+    "n_atom_basis": 64, "n_interactions": 3, "n_rbf": 32,
+    "cutoff_fn": {"__target__": "gotennet.models.components.layers.CosineCutoff", "cutoff": 5.0},
+    "radial_basis": "expnorm", "activation": "swish", "max_z": 100, "weight_init": "xavier_uniform",
+    "bias_init": "zeros", "num_heads": 8, "attn_dropout": 0.1, "edge_updates": True, "lmax": 2, "aggr": "add",
+    "scale_edge": False, "evec_dim": None, "emlp_dim": None, "sep_htr": True, "sep_dir": True, "sep_tensor": True,
+    "edge_ln": "",
+}
+
+
+def _lightning_ckpt(path, rep_state, extra_hp=None):
+    sd = {"representation." + k: v.clone() for k, v in rep_state.items()}
+    sd["output_modules.0.out_net.1.out_net.0.weight"] = torch.zeros(32, 64)   # task head entries are skipped
+    sd["output_modules.0.standardize.mean"] = torch.zeros(1)
+    hp = {"representation": dict(YAML_REPRESENTATION), "lr": 1e-4, "task": "QM9", "label": "U0"}
+    hp.update(extra_hp or {})
+    torch.save({"epoch": 3, "global_step": 1234, "pytorch-lightning_version": "2.4.0", "state_dict": sd,
+                "hyper_parameters": hp, "optimizer_states": [], "lr_schedulers": []}, path)
+
+
+def test_load_from_lightning_checkpoint(g, tmp_path):
+    """GotenNet.load_from_checkpoint (reference gotennet.py:904-946) on a Lightning-shaped .ckpt: `representation.`
+    prefix, `output_modules.*` present, Hydra node with `__target__` and a nested `cutoff_fn` target."""
+    cfg = orc.OracleConfig(n_atom_basis=64, n_interactions=3, lmax=2, sep_dir=True, sep_tensor=True, scale_edge=False)
+    src = orc.expand_aliases(orc.make_state_dict(cfg, seed=4))
+    path = str(tmp_path / "model.ckpt")
+    _lightning_ckpt(path, src)
+    m = g.GotenNetWrapper.load_from_checkpoint(path)
+    assert isinstance(m, g.GotenNetWrapper) and isinstance(m.cutoff_fn, g.CosineCutoff) and m.cutoff == 5.0
+    assert m.gata_list[0].dropout == 0.1 and m.sphere.l == 2 and m.hidden_dim == 64
+    got = m.state_dict()
+    assert set(got) == set(src) and all(torch.equal(got[k], src[k]) for k in src)
+    # nested form {"representation": {...}} (gotennet.py:921-922) and the `_target_` spelling
+    inner = torch.load(path, weights_only=False)
+    inner["hyper_parameters"]["representation"]["_target_"] = inner["hyper_parameters"]["representation"].pop("__target__")
+    torch.save({"representation": inner}, path)
+    m2 = g.GotenNetWrapper.load_from_checkpoint(path)
+    assert all(torch.equal(m2.state_dict()[k], src[k]) for k in src)
+    # error behaviour: missing file, missing keys, unknown nested target, stray state entries (strict)
+    with pytest.raises(FileNotFoundError):
+        g.GotenNet.load_from_checkpoint(str(tmp_path / "absent.ckpt"))
+    torch.save({"state_dict": {}}, path)
+    with pytest.raises(AssertionError):
+        g.GotenNet.load_from_checkpoint(path)
+    _lightning_ckpt(path, src)
+    bad = torch.load(path, weights_only=False)
+    bad["hyper_parameters"]["representation"]["cutoff_fn"]["__target__"] = "os.system"
+    torch.save(bad, path)
+    with pytest.raises(ValueError):
+        g.GotenNetWrapper.load_from_checkpoint(path)
+    _lightning_ckpt(path, {**src, "gata_list.0.not_a_key": torch.zeros(1)})
+    with pytest.raises(RuntimeError):
+        g.GotenNetWrapper.load_from_checkpoint(path)
+
+
+def test_checkpoint_round_trip_with_reference_module(g, tmp_path):
+    """A checkpoint written from the VERBATIM reference module's state_dict loads into ours bit-for-bit, and ours
+    loads back into the reference (build container only)."""
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("reference tree not present on this box")
+    from oracle.ref_standins import import_reference
+    ref = import_reference("/root/reference")
+    from gotennet.models.components.layers import CosineCutoff
+    kw = {k: v for k, v in YAML_REPRESENTATION.items() if k not in ("__target__", "cutoff_fn")}
+    torch.manual_seed(3)
+    rm = ref.GotenNetWrapper(cutoff_fn=CosineCutoff(5.0), **kw)
+    path = str(tmp_path / "ref.ckpt")
+    _lightning_ckpt(path, rm.state_dict())
+    m = g.GotenNetWrapper.load_from_checkpoint(path)
+    a, b = rm.state_dict(), m.state_dict()
+    assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    rm2 = ref.GotenNetWrapper(cutoff_fn=CosineCutoff(5.0), **kw)
+    rm2.load_state_dict(m.state_dict(), strict=True)

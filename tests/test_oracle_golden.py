@@ -161,3 +161,40 @@ def test_oracle_dropout_matches_reference_golden(golden_dir):
                 g = sd[k[5:]].grad
                 g = g if g is not None else torch.zeros_like(sd[k[5:]])
                 assert rel(grad_fingerprint(g), torch.from_numpy(gold[k])) < 1e-4, k
+
+
+# ------------------------------------------------ remaining QM9 heads --
+from oracle.golden_cases import HEAD2_CASES, head2_loss, head2_state  # noqa: E402
+
+
+@pytest.mark.parametrize("name", list(HEAD2_CASES))
+def test_oracle_heads2_match_reference_golden(name, golden_dir):
+    """Dipole / ElectronicSpatialExtentV2 restatements against the verbatim reference's outputs and gradients."""
+    from gotennet_b200.atomic_data import ATOMIC_MASSES
+    spec = HEAD2_CASES[name]
+    cfg, kind = spec["cfg"], spec["kind"]
+    gold = np.load(os.path.join(golden_dir, name + ".npz"))
+    z, pos, batch = blob(spec["atoms"], spec["seed"])
+    n_mol = len(spec["atoms"])
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "radial_basis" not in k)
+          for k, v in orc.make_state_dict(cfg, seed=spec["seed"]).items()}
+    sdh = {k: v.clone().requires_grad_(k.startswith(("out_net", "equivariant"))) for k, v in head2_state(spec).items()}
+    pos = pos.clone().requires_grad_(True)
+    h, X = orc.wrapper_forward(sd, cfg, z, pos, batch)
+    yv = None
+    if kind == "dipole":
+        y, yv = orc.dipole_forward(sdh, h, X, pos, batch, n_mol, mean=spec["mean"], stddev=spec["stddev"],
+                                   predict_magnitude=spec["predict_magnitude"])
+        assert rel(yv.detach(), gold["y_vector"]) < TOL
+    else:
+        y, x = orc.spatial_extent_forward(sdh, h, z, pos, batch, n_mol, torch.tensor(ATOMIC_MASSES))
+        assert rel(x.detach(), gold["contrib"]) < TOL
+    assert rel(y.detach(), gold["y"]) < TOL
+    head2_loss(kind, y, yv, n_mol).backward()
+    assert rel(pos.grad, gold["grad_pos"]) < TOL
+    for k in gold.files:
+        if k.startswith("gradh_"):
+            assert rel(grad_fingerprint(sdh[k[6:]].grad), gold[k]) < TOL, k
+        elif k.startswith("grad_") and k != "grad_pos":
+            g = sd[k[5:]].grad
+            assert rel(grad_fingerprint(g if g is not None else torch.zeros_like(sd[k[5:]])), gold[k]) < TOL, k

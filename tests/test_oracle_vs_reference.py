@@ -45,3 +45,11 @@ def test_head_fixture_regenerates_bit_identically(ref, golden_dir):
     from oracle.golden_cases import HEAD_CASES
     out = make_golden_head.run_case(ref, "head_forces_l2", HEAD_CASES["head_forces_l2"], save=False)
     _same(out, os.path.join(golden_dir, "head_forces_l2.npz"))
+
+
+def test_head2_fixture_regenerates_bit_identically(ref, golden_dir):
+    import make_golden_heads2
+    from oracle.golden_cases import HEAD2_CASES
+    for name in ("dipole_l2", "ese_l2"):
+        out = make_golden_heads2.run_case(ref, name, HEAD2_CASES[name], save=False)
+        _same(out, os.path.join(golden_dir, name + ".npz"))
