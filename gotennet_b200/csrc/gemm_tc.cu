@@ -90,7 +90,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   }
   tc_fence_before();
-  if (NCTA == 2) cluster_sync_all(); else __syncthreads();
+  __syncthreads();  // (the pair also meets below: compute-sanitizer racecheck only models the CTA barrier)
+  if (NCTA == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -247,7 +248,8 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 
   tc_fence_before();
-  if (NCTA == 2) cluster_sync_all(); else __syncthreads();   // the peer may still signal / read this CTA until here
+  __syncthreads();  // (the pair also meets below: compute-sanitizer racecheck only models the CTA barrier)
+  if (NCTA == 2) cluster_sync_all();   // the peer may still signal / read this CTA until here
   if (warp == 1) {
     tc_fence_after();
     if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));

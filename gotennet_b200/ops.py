@@ -821,8 +821,8 @@ class GatedEquivariantFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, scalars, vectors, Wmix, W1, b1, W2, b2, nso, nv, act, sact):
+        scalars, vectors = _f32(scalars.contiguous()), _f32(vectors.contiguous())  # X[:, :3] arrives as a strided view
         _chk(scalars, vectors, Wmix, W1, b1, W2, b2)
-        scalars, vectors = _f32(scalars.contiguous()), _f32(vectors.contiguous())
         N, ns = scalars.shape
         nvin = vectors.shape[2]
         if vectors.shape[:2] != (N, 3) or Wmix.shape != (2 * nv, nvin) or W2.shape[0] != nso + nv:
@@ -884,8 +884,8 @@ class DipoleAtomFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, l1, l0, pos, sd, mu):
-        _chk(l1, l0, pos)
         l1, l0, pos = _f32(l1.contiguous()), _f32(l0.contiguous()), _f32(pos.contiguous())
+        _chk(l1, l0, pos)
         N = l0.numel()
         yi = torch.empty(N, 3, device=l1.device)
         lib().call("goten_dipole_atom_fwd", _ptr(l1), _ptr(l0), _ptr(pos), float(sd), float(mu), N, _ptr(yi), _stream())
@@ -913,8 +913,8 @@ class RowNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, v):
-        _chk(v)
         v = _f32(v.contiguous())
+        _chk(v)
         M, D = v.shape
         y = torch.empty(M, 1, device=v.device)
         lib().call("goten_rownorm_fwd", _ptr(v), M, D, _ptr(y), _stream())
@@ -935,8 +935,8 @@ class SpatialExtentFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, pos, z, mass, mol_ptr, n_mol):
-        _chk(x, pos, z, mass, mol_ptr)
         x, pos = _f32(x.contiguous()), _f32(pos.contiguous())
+        _chk(x, pos, z, mass, mol_ptr)
         N = x.shape[0]
         dev = x.device
         yi = torch.empty(N, 1, device=dev)

@@ -11,11 +11,10 @@ TOOLS=${1:-"memcheck racecheck synccheck initcheck"}
 for tool in $TOOLS; do
   extra=""
   [ "$tool" = memcheck ] && extra="--leak-check no"
-  [ "$tool" = initcheck ] && extra="--track-unused-memory no"
   start=$(date +%s)
   timeout ${SAN_TIMEOUT:-900} compute-sanitizer --tool $tool $extra --print-limit 40 --error-exitcode 9 \
     --log-file gpurun_out/sanitizer_${tool}_raw.txt \
-    python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "$SEL" -p no:cacheprovider > gpurun_out/sanitizer_${tool}_pytest.txt 2>&1
+    python -m pytest tests/test_gpu_parity.py -m gpu -q -k "$SEL" -p no:cacheprovider > gpurun_out/sanitizer_${tool}_pytest.txt 2>&1
   rc=$?
   end=$(date +%s)
   {
