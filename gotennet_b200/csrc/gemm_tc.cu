@@ -37,7 +37,10 @@ struct Params {
   const float* bias;
   const float* add_src; int ld_add;
   float* act_out; int ld_act, act_lo, act_hi;
-  int add_vec, c_vec, act_vec;  // 16 B alignment of the add_src / C / act_out rows (vector epilogue accesses allowed)
+  int add_vec, c_vec, act_vec;
+  // 16 B alignment of the add_src / C / act_out rows (vector epilogue accesses allowed)
+  int red_add;            // add_src == C: accumulate into C with a TMA reduction store
+  int act_tma;            // SiLU side output through a second TMA store (tmAct)
   float* partial;         // split-K partials [splits][M][N] (nullptr: direct epilogue)
   float* colsum;          // column sums of A (MN-major only), direct
   float* partial_colsum;  // [splits][M]
@@ -46,7 +49,8 @@ struct Params {
 template <bool MN_MAJOR, int NCTA>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-              const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC, const Params p) {
+              const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
+              const __grid_constant__ CUtensorMap tmAct, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024 B alignment for the 128 B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -243,7 +247,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else {
     // =============================== epilogue (umma.cuh) ========================
-    gemm_epilogue<NCTA, BM, EPI_WARP0>(p, tmC, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
+    gemm_epilogue<NCTA, BM, EPI_WARP0>(p, tmC, tmAct, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
                                        n_tiles, BN, rank, 1.0f, 1.0f);
   }
 
@@ -449,7 +453,7 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
     GOTEN_CHECK_LAUNCH();
   }
 
-  CUtensorMap mA, mBh, mBl, mC;
+  CUtensorMap mA, mBh, mBl, mC, mAct;
   bool ok;
   if (!t.mn_major) {
     ok = make_map_kmajor(&mA, A, lda, M, K, tc::BM) && make_map_kmajor(&mBh, Bh, b_ld, N, K, t.block_n / t.ncta) &&
@@ -460,13 +464,21 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
   }
   GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d)", M, N, K, lda);
   // output map for the TMA-store epilogue: 32 x 32 blocks of C (or of the split-K partial buffer)
-  const bool fast_epi = t.splits > 1 || ((add_src == nullptr) && (act_out == nullptr));
+  const bool red_add = add_src != nullptr && add_src == C && ld_add == ldc && act_out == nullptr && t.splits == 1;
+  const bool act_tma = act_out != nullptr && t.splits == 1 && act_lo % 32 == 0 && act_hi > act_lo && aligned16(act_out) &&
+                       ld_act % 4 == 0 && (add_src == nullptr || red_add);
+  const bool fast_epi = t.splits > 1 || ((add_src == nullptr || red_add) && (act_out == nullptr || act_tma));
   if (t.splits > 1) ok = make_map_kmajor(&mC, partial, N, (int64_t)t.splits * M, N, 32);
   else if (fast_epi) {
     if (!aligned16(C) || ldc % 4 != 0) return 0;
     ok = make_map_kmajor(&mC, C, ldc, M, N, 32);
   } else mC = mA;  // unused by the fused epilogue path
   GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed for the output (M=%d N=%d ldc=%d)", M, N, ldc);
+  mAct = mC;
+  if (act_tma && t.splits == 1) {
+    ok = make_map_kmajor(&mAct, act_out, ld_act, M, act_hi - act_lo, 32);
+    GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed for the activation output (M=%d cols=%d ld=%d)", M, act_hi - act_lo, ld_act);
+  }
 
   tc::Params p{};
   p.M = M; p.N = N; p.K = K;
@@ -480,6 +492,8 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
   }
   p.C = C; p.ldc = ldc; p.bias = bias; p.add_src = add_src; p.ld_add = ld_add;
   p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
+  p.red_add = red_add ? 1 : 0;
+  p.act_tma = act_tma ? 1 : 0;
   p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
   p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
   p.act_vec = (act_out != nullptr && aligned16(act_out) && ld_act % 4 == 0 && act_lo % 4 == 0) ? 1 : 0;
@@ -512,7 +526,7 @@ int gemm_tc(const float* A, int lda, int trans_a, const float* B, int ldb, int t
       GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));   \
       smem_set = smem_optin;                                                                                \
     }                                                                                                       \
-    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, p));                                     \
+    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, mAct, p));                                     \
   } while (0)
   if (t.mn_major) {
     if (t.ncta == 2) GOTEN_TC_LAUNCH(true, 2); else GOTEN_TC_LAUNCH(true, 1);

@@ -86,6 +86,8 @@ struct Params {
   const float* add_src; int ld_add;
   float* act_out; int ld_act, act_lo, act_hi;
   int add_vec, c_vec, act_vec;
+  int red_add;            // add_src == C: accumulate into C with a TMA reduction store
+  int act_tma;            // SiLU side output through a second TMA store (tmAct)
   float* partial;
   float* colsum;
   float* partial_colsum;
@@ -98,7 +100,8 @@ struct Params {
 template <bool A_ROWS_ARE_K, bool B_RAW, int NCTA>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
-              const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC, const Params p) {
+              const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
+              const __grid_constant__ CUtensorMap tmAct, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int BN = p.block_n;
@@ -323,7 +326,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else {
     // =============================== epilogue (umma.cuh) ========================
-    gemm_epilogue<NCTA, BM, EPI_WARP0>(p, tmC, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
+    gemm_epilogue<NCTA, BM, EPI_WARP0>(p, tmC, tmAct, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
                                        n_tiles, BN, rank, inv_scale_of(*p.amax_a), inv_scale_of(*p.amax_b));
   }
 
@@ -638,7 +641,7 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   }
   if (!t.b_raw) GOTEN_CHECK_LAUNCH();
 
-  CUtensorMap mA, mBh, mBl, mC;
+  CUtensorMap mA, mBh, mBl, mC, mAct;
   bool ok;
   if (!t.a_rows_are_k) ok = make_map_f32(&mA, A, lda, M, K, 32, tc16::BM, CU_TENSOR_MAP_SWIZZLE_128B);
   else ok = make_map_f32(&mA, A, lda, K, M, tc16::BM, tc16::BK, CU_TENSOR_MAP_SWIZZLE_NONE);
@@ -649,13 +652,21 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     ok = ok && make_map_f16(&mBh, Bh, t.kp, N, K, t.block_n / t.ncta) && make_map_f16(&mBl, Bl, t.kp, N, K, t.block_n / t.ncta);
   }
   GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed (fp16 GEMM M=%d N=%d K=%d lda=%d)", M, N, K, lda);
-  const bool fast_epi = t.splits > 1 || ((add_src == nullptr) && (act_out == nullptr));
+  const bool red_add = add_src != nullptr && add_src == C && ld_add == ldc && act_out == nullptr && t.splits == 1;
+  const bool act_tma = act_out != nullptr && t.splits == 1 && act_lo % 32 == 0 && act_hi > act_lo && aligned16(act_out) &&
+                       ld_act % 4 == 0 && (add_src == nullptr || red_add);
+  const bool fast_epi = t.splits > 1 || ((add_src == nullptr || red_add) && (act_out == nullptr || act_tma));
   if (t.splits > 1) ok = make_map_f32(&mC, partial, N, (int64_t)t.splits * M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   else if (fast_epi) {
     if (!aligned16(C) || ldc % 4 != 0) return 0;
     ok = make_map_f32(&mC, C, ldc, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
   } else mC = mA;
   GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed for the output (M=%d N=%d ldc=%d)", M, N, ldc);
+  mAct = mC;
+  if (act_tma && t.splits == 1) {
+    ok = make_map_f32(&mAct, act_out, ld_act, M, act_hi - act_lo, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B);
+    GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed for the activation output (M=%d cols=%d ld=%d)", M, act_hi - act_lo, ld_act);
+  }
 
   tc16::Params p{};
   p.M = M; p.N = N; p.K = K;
@@ -664,6 +675,8 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   p.stages = t.stages;
   p.C = C; p.ldc = ldc; p.bias = bias; p.add_src = add_src; p.ld_add = ld_add;
   p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
+  p.red_add = red_add ? 1 : 0;
+  p.act_tma = act_tma ? 1 : 0;
   p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
   p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
   p.act_vec = (act_out != nullptr && aligned16(act_out) && ld_act % 4 == 0 && act_lo % 4 == 0) ? 1 : 0;
@@ -697,7 +710,7 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
       GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));   \
       smem_set = smem_optin;                                                                                \
     }                                                                                                       \
-    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, p));                                     \
+    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, mAct, p));                                     \
   } while (0)
   if (t.b_raw) {
     if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, true, 2); else GOTEN_TC16_LAUNCH(true, true, 1);

@@ -130,6 +130,13 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                "r"(c1)
                : "memory");
 }
+// global[tile] += smem tile (f32 add performed by the TMA unit at L2; every element is touched by exactly one
+// reduction, so the result is as deterministic as a plain store)
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
@@ -148,16 +155,21 @@ __device__ __forceinline__ float tf32_rna(float x) {
 //   fast path : one TMA store of the block (plain / bias / split-K partial outputs), double buffered
 //   fused path: read the block back row-wise and do coalesced global stores with the residual add and the SiLU side
 //               output (8 lanes x float4 = one 128 B row segment, 4 rows per instruction).
-// P needs: M, N, C, ldc, bias, add_src, ld_add, act_out, ld_act, act_lo, act_hi, add_vec, c_vec, act_vec, partial.
+// P needs: M, N, C, ldc, bias, add_src, ld_add, act_out, ld_act, act_lo, act_hi, add_vec, c_vec, act_vec, partial, red_add, act_tma.
 template <int NCTA, int BM, int EPI_WARP0, class P>
-__device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC, uint8_t* epi_smem, uint32_t bar_tfull,
+__device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC, const CUtensorMap& tmAct, uint8_t* epi_smem,
+                                              uint32_t bar_tfull,
                                               uint32_t bar_tempty, uint32_t tmem_base, int warp, int lane, int unit,
                                               int n_units, int n_items, int n_tiles, int BN, uint32_t rank, float un_a,
                                               float un_b) {
   // =============================== epilogue ===================================
   const int q = warp & 3;
   uint8_t* my_buf = epi_smem + (warp - EPI_WARP0) * 2 * 4096;
-  const bool fast = (p.add_src == nullptr) && (p.act_out == nullptr);
+  // red_add: the residual already sits in C (add_src == C): the tile is ADDED to it by a TMA reduction store, so the
+  // residual never passes through the SM (the register path below moves 4 KB per warp and round trip)
+  // act_tma: the SiLU side output (columns [act_lo, act_hi), act_lo a multiple of 32) leaves through a second TMA store of
+  // the same 32x32 block (tmAct is a map over act_out with act_hi - act_lo columns, so the range end clips for free)
+  const bool fast = (p.add_src == nullptr || p.red_add) && (p.act_out == nullptr || p.act_tma);
   uint32_t tile_it = 0, n_store = 0;
   for (int w = unit; w < n_items; w += n_units, ++tile_it) {
     const int split = w / n_tiles, tile = w % n_tiles;
@@ -204,10 +216,32 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
         __syncwarp();
         if (lane == 0) {
           if (p.partial) tma_store_2d(&tmC, smem_u32(buf), nc0, split * p.M + row_base);
+          else if (p.red_add) tma_reduce_add_2d(&tmC, smem_u32(buf), nc0, row_base);
           else tma_store_2d(&tmC, smem_u32(buf), nc0, row_base);
           bulk_commit();
         }
         ++n_store;
+        if (p.act_tma && nc0 >= p.act_lo && nc0 < p.act_hi) {   // warp-uniform: SiLU side output of this block
+          uint8_t* buf2 = my_buf + (n_store & 1) * 4096;
+          if (n_store >= 2) {
+            if (lane == 0) bulk_wait_read<1>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float4 v = *reinterpret_cast<const float4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
+            v.x = __fdividef(v.x, 1.0f + __expf(-v.x)); v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
+            v.z = __fdividef(v.z, 1.0f + __expf(-v.z)); v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+            *reinterpret_cast<float4*>(buf2 + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmAct, smem_u32(buf2), nc0 - p.act_lo, row_base);
+            bulk_commit();
+          }
+          ++n_store;
+        }
       } else {
         __syncwarp();
         const int cq = lane & 7, rsub = lane >> 3;

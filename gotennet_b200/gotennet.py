@@ -87,13 +87,16 @@ class GATA(nn.Module):
         parts = edge_updates.split("_") if isinstance(edge_updates, str) and edge_updates else []
         if not all(p in _ALLOWED_UPDATE_PARTS for p in parts):
             raise ValueError(f"Invalid edge update parts. Allowed parts are {_ALLOWED_UPDATE_PARTS}")
-        unsupported = [p for p in parts if p not in ("norej", "gated", "gatedt", "act", "mlp", "mlpa")]
+        # "norm" is accepted and ignored by the reference too (parsed at gotennet.py:149-161, never read again)
+        unsupported = [p for p in parts if p not in ("norej", "gated", "gatedt", "act", "mlp", "mlpa", "norm")]
         if unsupported:
             raise NotImplementedError(f"edge_updates parts {unsupported} are outside the accelerated path")
         if aggr != "add":
             raise NotImplementedError("only aggr='add' is implemented in the fused message kernel")
-        if edge_ln:
-            raise NotImplementedError("edge_ln is outside the accelerated path")
+        if edge_ln and ("mlp" in parts or "mlpa" in parts):
+            # reference layers.py:563-566: MLP puts `norm` on every Dense but the last, so edge_ln only exists inside a
+            # two-layer gamma_t; with the one-layer gamma_t it changes nothing (no module, no state_dict key)
+            raise NotImplementedError("edge_ln inside a two-layer gamma_t ('mlp' / 'mlpa') is outside the accelerated path")
         if evec_dim not in (None, n_atom_basis):
             raise NotImplementedError("evec_dim different from n_atom_basis needs the 'linw' edge update (not implemented)")
         if emlp_dim is not None and emlp_dim % 4 != 0:
@@ -128,7 +131,8 @@ class GATA(nn.Module):
             # the last one without ("mlp") or with ("mlpa") the activation
             two = self.update_info["mlp"] or self.update_info["mlpa"]
             self.gamma_t = MLP([C, self.edge_mlp_dim, C] if two else [C, C], activation=activation,
-                               last_activation=None if self.update_info["mlp"] else self.activation, norm=edge_ln,
+                               last_activation=None if self.update_info["mlp"] else self.activation,
+                               norm=edge_ln if two else "",
                                weight_init=weight_init, bias_init=bias_init)
             self.W_vq = mk(C, C, activation=None, bias=False)
             if self.sep_htr:
@@ -246,7 +250,8 @@ class GATA(nn.Module):
                 inv = torch.empty_like(plan.order)
                 inv[plan.order] = torch.arange(plan.E, device=inv.device)
                 t1 = t1[inv]
-            return h1.unsqueeze(1), ops.PermuteFn.apply(Xd1, False), t1
+            # (views: gradients arriving from a caller are then never overwritten by the in-place residual GEMMs)
+            return h1.unsqueeze(1), ops.PermuteFn.apply(Xd1, False), t1.view_as(t1)
 
 
 class EQFF(nn.Module):

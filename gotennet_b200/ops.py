@@ -101,6 +101,14 @@ def gemm(A, lda, ta, B, ldb, tb, C, ldc, M, N, K, *, a_off=0, b_off=0, c_off=0, 
            _stream())
 
 
+def _own(g) -> bool:
+    """True when an incoming gradient may be overwritten: a contiguous tensor that is not a view.  Inside the model
+    every such tensor is a temporary produced by the next block's backward (or by autograd's accumulation), so the
+    residual GEMMs  out = A B + g  accumulate straight into it (C == add_src: TMA reduction-store epilogue) instead
+    of reading it through the SMs.  Views (stand-alone module calls return views) take the out-of-place form."""
+    return g is not None and g._base is None and g.is_contiguous()
+
+
 def absmax(A, lda, M, N, *, a_off=0, out=None):
     """1-element device tensor holding max |A[m][n]| (no host sync); accumulates into `out` when given."""
     if out is None:
@@ -594,7 +602,7 @@ class GataBlockFn(torch.autograd.Function):
             # X gradient: g_Xm^l = g_Xd1^l + [g_EQ | g_EK]^l [W_vq; W_vk,l] (one K = 2C GEMM per degree group, the
             # residual added once); weight gradients of the stacked weight, un-stacked below
             G = len(cfg["vk_groups"])
-            g_Xm = torch.empty_like(Xd1)
+            g_Xm = g_Xd1 if _own(g_Xd1) else torch.empty_like(Xd1)   # in place: g_Xd1 is not read again
             dWqk = torch.empty_like(Wqk)
             for g, (lo, hi) in enumerate(cfg["vk_groups"]):
                 rows, off = (hi - lo) * N, lo * N * C
@@ -632,13 +640,13 @@ class GataBlockFn(torch.autograd.Function):
         gemm(g_v, SC, 1, A1, 2 * C, 0, dWv2, C, SC, C, N, b_off=C, colsum=dbv2, am=am)
         # through the SiLU of gamma_s.0 / gamma_v.0 into g_Z1[:, 2C:4C]
         dsilu_mul(g_A1, 2 * C, 0, Z1, 4 * C, 2 * C, g_Z1, 4 * C, 2 * C, N, 2 * C)
-        g_h = torch.empty_like(h)
+        g_h = g_h1 if _own(g_h1) else torch.empty_like(h)           # (the graph kernels above were its last readers)
         gemm(g_Z1, 4 * C, 0, Wn1, C, 0, g_h, C, N, C, 4 * C, add_src=g_h1, ld_add=C, am=am)
         dWn1 = torch.empty_like(Wn1)
         dbn1 = torch.empty(4 * C, device=dev)
         gemm(g_Z1, 4 * C, 1, h, C, 0, dWn1, C, 4 * C, C, N, colsum=dbn1, am=am)
         # edge projections
-        g_t = torch.empty_like(t)
+        g_t = g_t1 if (_own(g_t1) and E > 0) else torch.empty_like(t)
         dWe = torch.empty_like(We)
         dbe = torch.empty(ldz, device=dev)
         if E > 0:
@@ -704,7 +712,7 @@ class EqffBlockFn(torch.autograd.Function):
         am.put(g_P, gp_amax)
         L_.call("goten_eqff_ctx_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(g_cx), _ptr(P), _ptr(M), _ptr(cx), N, C, L,
                 _ptr(g_P), _ptr(g_h), _ptr(gp_amax), st)
-        g_Xd = torch.empty_like(Xd)
+        g_Xd = g_Xd2 if _own(g_Xd2) else torch.empty_like(Xd)
         gemm(g_P, C, 0, Wvu, C, 0, g_Xd, C, L * N, C, C, add_src=g_Xd2, ld_add=C, am=am)
         dWvu = torch.empty_like(Wvu)
         gemm(g_P, C, 1, Xd, C, 0, dWvu, C, C, C, L * N, am=am)

@@ -53,7 +53,9 @@ def test_state_dict_matches_reference_module(g):
     ref = import_reference(ref_root)
     from gotennet.models.components.layers import CosineCutoff
     for kw in (dict(n_atom_basis=64, n_interactions=2, lmax=1),
-               dict(n_atom_basis=32, n_interactions=3, lmax=3, sep_dir=True, sep_tensor=True, sep_htr=False)):
+               dict(n_atom_basis=32, n_interactions=3, lmax=3, sep_dir=True, sep_tensor=True, sep_htr=False),
+               # switches that are no-ops in the reference (no module, no key): "norm", edge_ln with a one-layer gamma_t
+               dict(n_atom_basis=32, n_interactions=2, lmax=2, edge_updates="norm_gated", edge_ln="layer")):
         a = ref.GotenNetWrapper(cutoff_fn=CosineCutoff(5.0), **kw).state_dict()
         b = g.GotenNetWrapper(cutoff_fn=g.CosineCutoff(5.0), **kw).state_dict()
         assert set(a) == set(b)
