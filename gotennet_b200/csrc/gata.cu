@@ -449,7 +449,8 @@ __global__ void gata_bwd_src_kernel(const float* __restrict__ g_h, const float* 
                                     const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src_perm,
                                     const int32_t* __restrict__ tgt, int N, int C, int H, float* __restrict__ g_qk,
                                     int ldgqk, float* __restrict__ g_x, float* __restrict__ g_v,
-                                    float* __restrict__ g_Xd_in) {
+                                    float* __restrict__ g_Xd_in, float* __restrict__ gx_amax,
+                                    float* __restrict__ gv_amax) {
   using Cf = GataCfg<LMAX, SD, ST>;
   constexpr int L = Cf::L, S = Cf::S, ND = Cf::ND;
   extern __shared__ float smem_f[];
@@ -542,10 +543,15 @@ __global__ void gata_bwd_src_kernel(const float* __restrict__ g_h, const float* 
   }
   if (act) {
 #pragma unroll
+    float ax = 0.f, av = 0.f;
     for (int k = 0; k < S; ++k) {
       stv<V>(g_x + (size_t)j * SC + k * C + c, gx[k]);
       stv<V>(g_v + (size_t)j * SC + k * C + c, gv[k]);
+#pragma unroll
+      for (int q = 0; q < V; ++q) { ax = fmaxf(ax, fabsf(gx[k][q])); av = fmaxf(av, fabsf(gv[k][q])); }
     }
+    amax_commit(gx_amax, ax);
+    amax_commit(gv_amax, av);
     stv<V>(g_qk + (size_t)j * ldgqk + C + c, gk);
 #pragma unroll
     for (int m = 0; m < L; ++m) {
@@ -591,7 +597,7 @@ int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, co
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                         const float* alpha, const float* da, const int32_t* src_ptr, const int32_t* src_perm,
                         const int32_t* tgt, int N, int C, int H, int lmax, int flags, float* g_qk, int ldgqk, float* g_x,
-                        float* g_v, float* g_Xd_in, cudaStream_t st, bool* handled);
+                        float* g_v, float* g_Xd_in, float* gx_amax, float* gv_amax, cudaStream_t st, bool* handled);
 
 // GOTEN_GATA=legacy forces the register-gather kernels of this file (A/B timing, tests)
 static bool use_staged() {
@@ -703,7 +709,8 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
                        const float* x, const float* v, const float* Ze, int ldz, const float* Y, const float* fc,
                        const float* kappa, const float* drop, const float* alpha, const float* da, const int32_t* src_ptr,
                        const int32_t* src_perm, const int32_t* tgt, int N, int C, int H, int lmax, int flags,
-                       float* g_qk, int ldgqk, float* g_x, float* g_v, float* g_Xd_in, void* stream) {
+                       float* g_qk, int ldgqk, float* g_x, float* g_v, float* g_Xd_in, float* gx_amax, float* gv_amax,
+                       void* stream) {
   const int V = (gata_vec(C, H, ldqk, ldz) == 4 && ldgqk % 4 == 0) ? 4 : 1;
   if (gata_check(C, H, lmax, V)) return 1;
   if (N == 0) return 0;
@@ -711,14 +718,14 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
   if (use_staged()) {
     bool handled = false;
     if (gata_bwd_src_staged(g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, da, src_ptr, src_perm, tgt, N, C,
-                            H, lmax, flags, g_qk, ldgqk, g_x, g_v, g_Xd_in, st, &handled))
+                            H, lmax, flags, g_qk, ldgqk, g_x, g_v, g_Xd_in, gx_amax, gv_amax, st, &handled))
       return 1;
     if (handled) return 0;
   }
   const int L = (lmax + 1) * (lmax + 1) - 1;
   const size_t smem = (size_t)SRC_CHUNK * (4 + L + 2 * H) * sizeof(float);
   GATA_DISPATCH(gata_bwd_src_kernel, N, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, da,
-                src_ptr, src_perm, tgt, N, C, H, g_qk, ldgqk, g_x, g_v, g_Xd_in);
+                src_ptr, src_perm, tgt, N, C, H, g_qk, ldgqk, g_x, g_v, g_Xd_in, gx_amax, gv_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

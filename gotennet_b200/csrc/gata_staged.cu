@@ -512,7 +512,8 @@ __global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const 
                                            const int32_t* __restrict__ src_ptr, const int32_t* __restrict__ src_perm,
                                            const int32_t* __restrict__ tgt, int N, int C, int H, int R,
                                            float* __restrict__ g_qk, int ldgqk, float* __restrict__ g_x,
-                                           float* __restrict__ g_v, float* __restrict__ g_Xd_in) {
+                                           float* __restrict__ g_v, float* __restrict__ g_Xd_in,
+                                           float* __restrict__ gx_amax, float* __restrict__ gv_amax) {
   using Cf = Cfg<LMAX, SD, ST>;
   constexpr int L = Cf::L, S = Cf::S, ND = Cf::ND, NT = Cf::NT;
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -642,11 +643,16 @@ __global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const 
     }
   }
   if (!act) return;
+  float ax = 0.f, av = 0.f;  // running max |g_x|, |g_v|: operand scales of the gamma_s.1 / gamma_v.1 gradient GEMMs
 #pragma unroll
   for (int k = 0; k < S; ++k) {
     st4(g_x + (size_t)j * SC + k * C + c, gx[k]);
     st4(g_v + (size_t)j * SC + k * C + c, gv[k]);
+    ax = amax4(ax, gx[k].x, gx[k].y, gx[k].z, gx[k].w);
+    av = amax4(av, gv[k].x, gv[k].y, gv[k].z, gv[k].w);
   }
+  amax_commit(gx_amax, ax);
+  amax_commit(gv_amax, av);
   st4(g_qk + (size_t)j * ldgqk + C + c, gk);
 #pragma unroll
   for (int m = 0; m < L; ++m) {
@@ -784,7 +790,7 @@ int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, co
                         const float* v, const float* Ze, int ldz, const float* Y, const float* fc, const float* kappa, const float* drop,
                         const float* alpha, const float* da, const int32_t* src_ptr, const int32_t* src_perm,
                         const int32_t* tgt, int N, int C, int H, int lmax, int flags, float* g_qk, int ldgqk, float* g_x,
-                        float* g_v, float* g_Xd_in, cudaStream_t st, bool* handled) {
+                        float* g_v, float* g_Xd_in, float* gx_amax, float* gv_amax, cudaStream_t st, bool* handled) {
   *handled = false;
   const int D = C / H;
   if (C % 4 != 0 || D % 4 != 0 || ldqk % 4 != 0 || ldz % 4 != 0 || ldgqk % 4 != 0) return 0;
@@ -803,7 +809,7 @@ int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   if (R * stage_bytes + tail > 220 * 1024) return 0;
   const size_t smem = R * stage_bytes + tail;
   STAGED_DISPATCH(gata_bwd_src_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha,
-                  da, src_ptr, src_perm, tgt, N, C, H, R, g_qk, ldgqk, g_x, g_v, g_Xd_in);
+                  da, src_ptr, src_perm, tgt, N, C, H, R, g_qk, ldgqk, g_x, g_v, g_Xd_in, gx_amax, gv_amax);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
   return 0;

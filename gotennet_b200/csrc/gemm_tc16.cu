@@ -466,6 +466,38 @@ split16_transpose_direct_kernel(const float* __restrict__ in, int ld, int rows /
   }
 }
 
+// up to 16 contiguous tensors in one launch: blockIdx.y = tensor, grid-stride over its elements
+struct AbsmaxMulti {
+  const float* ptr[16];
+  int64_t n[16];
+};
+__global__ void __launch_bounds__(256) absmax_multi_kernel(AbsmaxMulti a, float* __restrict__ out) {
+  __shared__ float red[8];
+  const float* __restrict__ p = a.ptr[blockIdx.y];
+  const int64_t n = a.n[blockIdx.y];
+  float m = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const float4* p4 = reinterpret_cast<const float4*>(p);
+    for (int64_t i = idx; i < (n >> 2); i += stride) {
+      const float4 v = p4[i];
+      m = amax4(m, v.x, v.y, v.z, v.w);
+    }
+    for (int64_t i = ((n >> 2) << 2) + idx; i < n; i += stride) m = fmaxf(m, fabsf(p[i]));
+  } else {
+    for (int64_t i = idx; i < n; i += stride) m = fmaxf(m, fabsf(p[i]));
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0 && m > 0.f) atomicMax(reinterpret_cast<unsigned int*>(out + blockIdx.y), __float_as_uint(m));
+  }
+}
+
 }  // namespace tc16
 
 int splitk_finish(const float* partial, const float* partial_cs, int splits, float* C, int ldc, int M, int N,
@@ -735,6 +767,23 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
 using namespace goten;
 
 extern "C" {
+
+int goten_absmax_multi(const float* const* ptrs, const int64_t* numel, int count, float* out, void* stream) {
+  GOTEN_REQUIRE(count >= 0 && count <= 16, "goten_absmax_multi takes at most 16 tensors (got %d)", count);
+  if (count == 0) return 0;
+  tc16::AbsmaxMulti a{};
+  int64_t nmax = 0;
+  for (int i = 0; i < count; ++i) {
+    a.ptr[i] = ptrs[i];
+    a.n[i] = numel[i];
+    nmax = numel[i] > nmax ? numel[i] : nmax;
+  }
+  int64_t gx = cdiv64(nmax, 256 * 16);
+  gx = gx < 1 ? 1 : (gx > 64 ? 64 : gx);
+  tc16::absmax_multi_kernel<<<dim3((unsigned)gx, (unsigned)count), 256, 0, as_stream(stream)>>>(a, out);
+  GOTEN_CHECK_LAUNCH();
+  return 0;
+}
 
 int goten_absmax(const float* A, int64_t lda, int64_t M, int N, float* out, void* stream) {
   if (M <= 0 || N <= 0) return 0;

@@ -149,6 +149,26 @@ class AmaxScope:
             self._d[T.data_ptr()] = ent
         return ent[1]
 
+    def prefetch(self, tensors):
+        """max |T| of several contiguous tensors (the weight matrices of a block) in ONE launch instead of one pass
+        each; tensors already known are skipped."""
+        if not self.enabled:
+            return
+        todo = [T for T in tensors if T is not None and T.data_ptr() not in self._d and T.is_contiguous()][:16]
+        if len(todo) < 2:
+            return
+        dev = todo[0].device
+        if self._pool is None or self._used + len(todo) > self._pool.numel() or self._pool.device != dev:
+            self._pool, self._used = torch.zeros(32, device=dev, dtype=torch.float32), 0
+        out = self._pool[self._used:self._used + len(todo)]
+        self._used += len(todo)
+        import ctypes
+        ptrs = (ctypes.c_void_p * len(todo))(*[T.data_ptr() for T in todo])
+        nums = (ctypes.c_int64 * len(todo))(*[T.numel() for T in todo])
+        lib().call("goten_absmax_multi", ctypes.addressof(ptrs), ctypes.addressof(nums), len(todo), _ptr(out), _stream())
+        for i, T in enumerate(todo):
+            self._d[T.data_ptr()] = (T, out[i:i + 1])
+
     def export(self, tensors):
         """amax tensors (or an empty list when inert) of `tensors`, in order; None entries are skipped."""
         if not self.enabled:
@@ -473,6 +493,11 @@ class GataBlockFn(torch.autograd.Function):
         SC = S * C
         am = AmaxScope()
         am.put(t, t_amax)  # max |t| from the kernel that produced t (None: measured on first use)
+        Wqk = None
+        if htr:
+            # [W_vq; W_vk,l] stacked per degree group (one GEMM per group below)
+            Wqk = torch.cat([Wvq.unsqueeze(0).expand(len(cfg["vk_groups"]), C, C), Wvk], dim=1).contiguous()  # [G][2C][C]
+        am.prefetch([Wn1, Ws2, Wv2, We, Wqk, Wt2])  # all weight maxima of the block in one launch
         # node projections: Z1 = [q | k | pre_s | pre_v], A1 = silu(Z1[:, 2C:])
         Z1 = torch.empty(N, 4 * C, device=dev)
         A1 = torch.empty(N, 2 * C, device=dev)
@@ -502,13 +527,12 @@ class GataBlockFn(torch.autograd.Function):
         L_.call("goten_gata_fwd", _ptr(h), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze), ldz, _ptr(Y),
                 _ptr(fc), _ptr(kappa), _ptr(drop), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax, cfg["gata_flags"],
                 plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), _ptr(xd_amax), st)
-        EQK = Wqk = None
+        EQK = None
         t1 = t
         if htr:
             # EQ = W_vq X and EK^l = W_vk,l X^l (gotennet.py:432-441) as ONE GEMM per degree group with the stacked
             # weight [W_vq; W_vk,l]: rows of EQK are [EQ | EK] (pitch 2C), X is read once
             G = len(cfg["vk_groups"])
-            Wqk = torch.cat([Wvq.unsqueeze(0).expand(G, C, C), Wvk], dim=1).contiguous()  # [G][2C][C]
             EQK = torch.empty(L, N, 2 * C, device=dev)
             for g, (lo, hi) in enumerate(cfg["vk_groups"]):
                 rows = (hi - lo) * N
@@ -622,12 +646,16 @@ class GataBlockFn(torch.autograd.Function):
                 _ptr(g_Y), _ptr(gze_amax), st)
         g_x = torch.empty(N, SC, device=dev)
         g_v = torch.empty(N, SC, device=dev)
+        gx_amax = am.slot(dev) if am.enabled else None   # written by the kernel that fills g_x / g_v
+        gv_amax = am.slot(dev) if am.enabled else None
+        am.put(g_x, gx_amax)
+        am.put(g_v, gv_amax)
         g_Xd = torch.empty_like(Xd)
         L_.call("goten_gata_bwd_src", _ptr(g_h1), _ptr(g_Xm), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze),
                 ldz, _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(drop), _ptr(alpha), _ptr(da), _ptr(plan.src_ptr),
                 _ptr(plan.src_perm),
                 _ptr(plan.tgt), N, C, H, lmax, cfg["gata_flags"], _ptr(g_Z1), 4 * C, _ptr(g_x), _ptr(g_v),
-                _ptr(g_Xd), st)
+                _ptr(g_Xd), _ptr(gx_amax), _ptr(gv_amax), st)
         # gamma_s.1 / gamma_v.1
         g_A1 = torch.empty(N, 2 * C, device=dev)
         gemm(g_x, SC, 0, Ws2, C, 0, g_A1, 2 * C, N, C, SC, am=am)
@@ -673,6 +701,7 @@ class EqffBlockFn(torch.autograd.Function):
         dev = h.device
         am = AmaxScope()
         am.put(Xd, xd_amax)  # max |Xd| from the GATA kernel that produced it (None: measured on first use)
+        am.prefetch([Wvu, Wm1, Wm2])
         P = torch.empty_like(Xd)
         gemm(Xd, C, 0, Wvu, C, 1, P, C, L * N, C, C, am=am)
         cx = torch.empty(N, 2 * C, device=dev)

@@ -139,6 +139,10 @@ int goten_gemm_scaled(const float* A, int lda, int trans_a, const float* B, int 
  * out[0] = max(out[0], max |A[m][n]|) over a [M][N] matrix (ld = lda); out must hold a
  * non-negative float (zero it first for a plain maximum).                                */
 int goten_absmax(const float* A, int64_t lda, int64_t M, int N, float* out, void* stream);
+/* The same for up to 16 CONTIGUOUS tensors in one launch (the weight matrices of a block):
+ * out[i] = max(out[i], max |ptrs[i][0 .. numel[i])|); ptrs / numel are HOST arrays.          */
+int goten_absmax_multi(const float* const* ptrs, const int64_t* numel, int count, float* out,
+                       void* stream);
 /* out[m][n] = g[m][n] * silu'(pre[m][n])  (Dense activation backward, layers.py:527-528) */
 int goten_dsilu_mul(const float* g, int ldg, const float* pre, int ldp, float* out, int ldo,
                     int64_t M, int N, void* stream);
@@ -223,14 +227,17 @@ int goten_gata_bwd_tgt(const float* g_h, const float* g_Xd, const float* Xd, con
                        int lmax, int flags, int max_deg_in, float* g_qk, int ldgqk, float* gZe,
                        int ldgz, float* da, float* g_fc, float* g_Y, float* gze_amax, void* stream);
 /* backward, source-centric half: g_qk[:, C:2C) (dk), g_x, g_v [N][S*C] and
- * g_Xd_in[L][N][C] = g_Xd + sum over outgoing edges (residual included).      */
+ * g_Xd_in[L][N][C] = g_Xd + sum over outgoing edges (residual included).
+ * gx_amax / gv_amax (optional, device, zeroed by the caller): running max |g_x| / |g_v|,
+ * the operand bounds of the gamma_s.1 / gamma_v.1 gradient GEMMs.               */
 int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, const float* qk,
                        int ldqk, const float* x, const float* v, const float* Ze, int ldz,
                        const float* Y, const float* fc, const float* kappa, const float* drop,
                        const float* alpha,
                        const float* da, const int32_t* src_ptr, const int32_t* src_perm,
                        const int32_t* tgt, int n_nodes, int C, int H, int lmax, int flags,
-                       float* g_qk, int ldgqk, float* g_x, float* g_v, float* g_Xd_in, void* stream);
+                       float* g_qk, int ldgqk, float* g_x, float* g_v, float* g_Xd_in, float* gx_amax,
+                       float* gv_amax, void* stream);
 
 /* ------------------------------------------------------------- HTR block --
  * GATA.edge_update + vector_rejection + residual (gotennet.py:351-364, :561-611,

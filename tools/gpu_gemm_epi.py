@@ -35,6 +35,9 @@ cases = [  # (label, M, N, K, trans_b, add, act)
     ("node proj + silu side", Nn, 1024, 256, 1, False, True),
     ("eqff gamma_m.0 + silu", Nn, 256, 512, 1, False, True),
     ("eqff W_vu fwd (plain)", 8 * Nn, 256, 256, 1, False, False),
+    ("edge fwd W_re|W_rs|g_t", E, 1792, 256, 1, False, False),
+    ("gamma_s.1 fwd (plain)", Nn, 1280, 256, 1, False, False),
+    ("htr EQ|EK fwd (plain)", 5 * Nn, 512, 256, 1, False, False),
 ]
 for label, M, N, K, tb, add, act in cases:
     a = torch.randn(M, K, device=dev)
