@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIBNAME = "libgotennet_b200.so"
-SOURCES = ["graph.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc16.cu", "init.cu", "gata.cu", "gata_staged.cu", "htr.cu", "eqff.cu", "readout.cu", "heads.cu", "optim.cu", "norm.cu"]
+SOURCES = ["graph.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc16.cu", "init.cu", "gata.cu", "gata_staged.cu", "edge_fused.cu", "htr.cu", "eqff.cu", "readout.cu", "heads.cu", "optim.cu", "norm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

@@ -31,50 +31,6 @@ constexpr int NTHREADS = 320;
 constexpr int EPI_WARP0 = 2, CONV_WARP0 = 6;
 constexpr uint32_t A_BYTES = BM * BK * 4;   // raw fp32 tile = hi + lo fp16 tiles = 32 KB
 
-// power-of-two scale that maps a tensor maximum into [2^14, 2^15), and its inverse (both exact floats)
-__device__ __forceinline__ float scale_of(float amax) {
-  const int e = (int)((__float_as_uint(amax) >> 23) & 0xFF);
-  if (amax == 0.f || e == 255) return 1.0f;
-  int sb = 268 - e;  // biased exponent of 2^(14 - (e - 127))
-  sb = sb < 1 ? 1 : (sb > 253 ? 253 : sb);
-  return __uint_as_float((uint32_t)sb << 23);
-}
-__device__ __forceinline__ float inv_scale_of(float amax) {
-  const float s = scale_of(amax);
-  return __uint_as_float((uint32_t)(254 - (int)(__float_as_uint(s) >> 23)) << 23);
-}
-
-// hi/lo split of two scaled values -> packed half2 words
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
 struct Params {
   int M, N, K;
   int block_n;

@@ -15,6 +15,7 @@ our control.
 from __future__ import annotations
 
 import contextlib
+import ctypes
 import os
 from typing import Optional
 
@@ -512,21 +513,34 @@ class GataBlockFn(torch.autograd.Function):
         two = Wt2 is not None                       # two-layer gamma_t
         Em = ldz - (S + 1) * C                      # width of gamma_t's first layer (0 on the last block)
         A_t = torch.empty(E, Em, device=dev) if two else None   # SiLU of its pre-activation, input of the second layer
-        if E > 0:
-            if two:
-                gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, act_out=A_t, ld_act=Em, act_lo=(S + 1) * C,
-                     act_hi=ldz, am=am)
-            else:
-                gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, am=am)
         h1 = torch.empty_like(h)
         Xd1 = torch.empty_like(Xd)
         alpha = torch.empty(E, H, device=dev)
         hints = torch.zeros(2, device=dev)  # [max |Xd1|, max |t1|], written by the producing kernels
         xd_amax, t1_amax = hints[0:1], hints[1:2]
         am.put(Xd1, xd_amax)
-        L_.call("goten_gata_fwd", _ptr(h), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze), ldz, _ptr(Y),
-                _ptr(fc), _ptr(kappa), _ptr(drop), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax, cfg["gata_flags"],
-                plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), _ptr(xd_amax), st)
+        fused = ctypes.c_int(0)
+        if E > 0 and not two and am.enabled:
+            # ONE kernel for projections + attention + messages (edge_fused.cu): the projection tile is consumed from
+            # tensor memory; Ze is written in full only when a backward will read it, else just gamma_t's columns
+            training = any(ctx.needs_input_grad)
+            nb = L_.cdll.goten_gata_fused_workspace_bytes(C, ldz)
+            ws = workspace(nb, dev)
+            L_.call("goten_gata_fused_fwd", _ptr(t), _ptr(We), _ptr(be), _ptr(am.of(t)), _ptr(am.of(We)), _ptr(h),
+                    _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Y), _ptr(fc), _ptr(kappa), _ptr(drop),
+                    _ptr(plan.tgt_ptr), _ptr(plan.src), N, E, C, H, lmax, cfg["gata_flags"], plan.max_deg_in, ldz,
+                    0 if training else (S + 1) * C, _ptr(Ze), _ptr(alpha), _ptr(h1), _ptr(Xd1), _ptr(xd_amax), _ptr(ws),
+                    ws.numel(), ctypes.addressof(fused), st)
+        if not fused.value:
+            if E > 0:
+                if two:
+                    gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, act_out=A_t, ld_act=Em, act_lo=(S + 1) * C,
+                         act_hi=ldz, am=am)
+                else:
+                    gemm(t, C, 0, We, C, 1, Ze, ldz, E, ldz, C, bias=be, am=am)
+            L_.call("goten_gata_fwd", _ptr(h), _ptr(Xd), _ptr(Z1), 4 * C, _ptr(x), _ptr(v), _ptr(Ze), ldz, _ptr(Y),
+                    _ptr(fc), _ptr(kappa), _ptr(drop), _ptr(plan.tgt_ptr), _ptr(plan.src), N, C, H, lmax,
+                    cfg["gata_flags"], plan.max_deg_in, _ptr(h1), _ptr(Xd1), _ptr(alpha), _ptr(xd_amax), st)
         EQK = None
         t1 = t
         if htr:

@@ -213,6 +213,22 @@ int goten_gata_fwd(const float* h, const float* Xd, const float* qk, int ldqk, c
                    int n_nodes,
                    int C, int H, int lmax, int flags, int max_deg_in, float* h_out, float* Xd_out,
                    float* alpha, float* xd_amax, void* stream);
+/* Fused forward of the edge path (edge_fused.cu): the edge projections  t @ [W_re | W_rs | gamma_t]^T  (gotennet.py:
+ * 406-407, :611), the attention softmax and the message aggregation of goten_gata_fwd in ONE kernel - the projection
+ * tile stays in tensor memory (tcgen05, transposed product: TMEM lane = channel, column = edge) and is consumed by
+ * the epilogue, so Ze is written only from column `store_from` on (0: everything, for the backward; (S+1)*C: only
+ * gamma_t's pre-activations, for inference).  We [ldz][C], be [ldz]; t_amax / w_amax: device bounds of max|t| / max|We|.
+ * *handled = 0 (and nothing launched) when the layout is outside the kernel's contract (head width 32, C % 128 == 0,
+ * in-degree <= 96, per-degree chunks): the caller then runs goten_gemm_scaled + goten_gata_fwd.                       */
+int64_t goten_gata_fused_workspace_bytes(int C, int ldz);
+int goten_gata_fused_fwd(const float* t, const float* We, const float* be, const float* t_amax,
+                         const float* w_amax, const float* h, const float* Xd, const float* qk, int ldqk,
+                         const float* x, const float* v, const float* Y, const float* fc,
+                         const float* kappa, const float* drop, const int32_t* tgt_ptr, const int32_t* src,
+                         int n_nodes, int64_t n_edges, int C, int H, int lmax, int flags, int max_deg_in,
+                         int ldz, int store_from, float* Ze, float* alpha, float* h_out, float* Xd_out,
+                         float* xd_amax, void* workspace, int64_t workspace_bytes, int* handled,
+                         void* stream);
 /* backward, target-centric half: needs g_h[N][C], g_Xd[L][N][C] (gradients of the
  * block outputs).  Produces g_qk[:, 0:C) (dq), gZe[:, 0:(S+1)C) (d pre-act W_re, d filter),
  * da[E][H] (gradient of the attention logits) and, if non-NULL, the geometry

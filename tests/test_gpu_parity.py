@@ -750,3 +750,49 @@ def test_dipole_and_spatial_extent_heads_golden(g, dev, name, golden_dir):
             assert rel(grad_fingerprint(gr.cpu()), gold[k]) < TOL, k
             n += 1
     assert n == len(hp) + len(orc.state_dict_spec(cfg))
+
+
+@pytest.mark.gpu
+def test_fused_edge_kernel_matches_oracle_and_unfused(g, dev, monkeypatch):
+    """Opt-in fused edge kernel (edge_fused.cu, GOTEN_EDGE_FUSED=1: edge projections + attention softmax + message
+    aggregation in one tcgen05 kernel, Ze consumed from tensor memory) at C=256 / head width 32: forward and every
+    gradient against the CPU oracle, bit-for-bit attention weights vs the three-kernel sequence is NOT required (different
+    summation order) but agreement to 1e-5 is; inference mode (only gamma_t's columns of Ze are stored) equals the
+    training forward exactly."""
+    cfg = orc.OracleConfig(n_atom_basis=256, n_interactions=3, lmax=2, sep_dir=True, sep_tensor=True, scale_edge=False)
+    z, pos, batch = orc.synth_batch("qm9", 5, seed=13)
+    sd = orc.make_state_dict(cfg, seed=3)
+    m = build(g, cfg, sd, dev)
+
+    def run(fused, grad=True):
+        monkeypatch.setenv("GOTEN_EDGE_FUSED", "1" if fused else "0")
+        for p in m.parameters():
+            p.grad = None
+        d = make_data(z, pos, batch, dev, grad=grad)
+        if not grad:
+            with torch.no_grad():
+                return m(d)
+        h, X = m(d)
+        (h.sum() + X.pow(2).sum()).backward()
+        return h.detach(), X.detach(), d.pos.grad.clone(), {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    from gotennet_b200._lib import lib
+    n0 = lib().cdll.goten_launch_count()
+    h1, X1, gp1, g1 = run(True)
+    n_fused = lib().cdll.goten_launch_count() - n0
+    n0 = lib().cdll.goten_launch_count()
+    h0, X0, gp0, g0 = run(False)
+    assert lib().cdll.goten_launch_count() - n0 > n_fused          # the fused path really replaced launches
+    assert rel(h1, h0) < 1e-5 and rel(X1, X0) < 1e-5 and rel(gp1, gp0) < 1e-5
+    assert max(rel(g1[k], g0[k]) for k in g0) < 1e-5
+    sdo = _oracle_leaf_state(sd)
+    pos_o = pos.clone().requires_grad_(True)
+    ho, Xo = orc.wrapper_forward(sdo, cfg, z, pos_o, batch)
+    (ho.sum() + Xo.pow(2).sum()).backward()
+    assert rel(h1, ho.detach()) < TOL and rel(X1, Xo.detach()) < TOL and rel(gp1, pos_o.grad) < TOL
+    keys = [k for k, _, _ in orc.state_dict_spec(cfg)]
+    for k in keys:
+        go = sdo[k].grad if sdo[k].grad is not None else torch.zeros_like(sdo[k])
+        assert rel(g1[k], go) < TOL, k
+    hi, Xi = run(True, grad=False)
+    assert torch.equal(hi, h1) and torch.equal(Xi, X1)
