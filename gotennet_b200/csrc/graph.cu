@@ -314,7 +314,7 @@ __global__ void edge_geometry_bwd_kernel(const float* __restrict__ r_in, const f
                                          int64_t E, float rc, int R, int basis, const float* __restrict__ means,
                                          const float* __restrict__ betas, const float* __restrict__ g_phi,
                                          const float* __restrict__ g_fc, const float* __restrict__ g_Y,
-                                         float* __restrict__ g_vec) {
+                                         const float* __restrict__ g_r_in, float* __restrict__ g_vec) {
   constexpr int L = (LMAX + 1) * (LMAX + 1) - 1;
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
@@ -329,7 +329,7 @@ __global__ void edge_geometry_bwd_kernel(const float* __restrict__ r_in, const f
   const bool inside = r < rc;
   const float fc = inside ? 0.5f * (cosf(r * pi_rc) + 1.0f) : 0.f;
   const float dfc = inside ? -0.5f * sinf(r * pi_rc) * pi_rc : 0.f;
-  float g_r = g_fc ? g_fc[e] * dfc : 0.f;
+  float g_r = (g_fc ? g_fc[e] * dfc : 0.f) + (g_r_in ? g_r_in[e] : 0.f);   // g_r_in: gradient of the returned distance itself
   if (g_phi && basis == 0) {
     const float alpha = 5.0f / rc;
     const float ex = expf(-alpha * r);
@@ -533,7 +533,8 @@ int goten_edge_geometry_fwd(const float* pos, const float* edge_vec_in, const fl
 
 int goten_edge_geometry_bwd(const float* r, const float* u, const int32_t* src, const int32_t* tgt, int64_t E,
                             int lmax, float cutoff, int n_rbf, int basis, const float* means, const float* betas,
-                            const float* g_phi, const float* g_fc, const float* g_Y, float* g_vec, void* stream) {
+                            const float* g_phi, const float* g_fc, const float* g_Y, const float* g_r, float* g_vec,
+                            void* stream) {
   if (E == 0) return 0;
   GOTEN_REQUIRE(lmax >= 1 && lmax <= 3, "lmax=%d unsupported (1..3)", lmax);
   cudaStream_t st = as_stream(stream);
@@ -541,7 +542,7 @@ int goten_edge_geometry_bwd(const float* r, const float* u, const int32_t* src, 
   const unsigned nb = (unsigned)cdiv64(E, T);
 #define LAUNCH(LM)                                                                                        \
   edge_geometry_bwd_kernel<LM><<<nb, T, 0, st>>>(r, u, src, tgt, E, cutoff, n_rbf, basis, means, betas, g_phi,    \
-                                                g_fc, g_Y, g_vec)
+                                                g_fc, g_Y, g_r, g_vec)
   if (lmax == 1) LAUNCH(1); else if (lmax == 2) LAUNCH(2); else LAUNCH(3);
 #undef LAUNCH
   GOTEN_CHECK_LAUNCH();

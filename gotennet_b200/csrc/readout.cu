@@ -88,6 +88,17 @@ __global__ void atomwise_reduce_bwd_kernel(const float* __restrict__ g_y, const 
   }
 }
 
+// mode 0 (no aggregation): g_raw = (g_y + g_yi) * stddev, element-wise
+__global__ void atomwise_scale_bwd_kernel(const float* __restrict__ g_y, const float* __restrict__ g_yi,
+                                          const float* __restrict__ stddev, int n_stat, int64_t total, int n_out,
+                                          float* __restrict__ g_raw) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int o = (int)(idx % n_out);
+  const float g = (g_y ? g_y[idx] : 0.f) + (g_yi ? g_yi[idx] : 0.f);
+  g_raw[idx] = g * (stddev ? stddev[n_stat > 1 ? o : 0] : 1.f);
+}
+
 // element-wise activations of the head MLP: kind 1 = SiLU, 2 = shifted softplus ln(1 + e^x) - ln 2
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // torch threshold = 20
 __global__ void act_fwd_kernel(int kind, const float* __restrict__ x, int64_t n, float* __restrict__ y) {
@@ -151,8 +162,15 @@ int goten_atomwise_reduce_fwd(const float* raw, const int64_t* z, const float* a
 int goten_atomwise_reduce_bwd(const float* g_y, const float* g_yi, const float* stddev, int n_stat,
                               const int32_t* mol_ptr, int n_nodes, int n_mol, int n_out, int mode, float* g_raw,
                               void* stream) {
-  GOTEN_REQUIRE(mode >= 1 && mode <= 2, "aggregation mode %d unsupported in the segmented backward", mode);
+  GOTEN_REQUIRE(mode >= 0 && mode <= 2, "aggregation mode %d unsupported in the backward", mode);
   cudaStream_t st = as_stream(stream);
+  if (mode == 0) {   // no aggregation: y is yi, both gradients add element-wise
+    const int64_t tot = (int64_t)n_nodes * n_out;
+    if (tot == 0) return 0;
+    atomwise_scale_bwd_kernel<<<(unsigned)cdiv64(tot, 256), 256, 0, st>>>(g_y, g_yi, stddev, n_stat, tot, n_out, g_raw);
+    GOTEN_CHECK_LAUNCH();
+    return 0;
+  }
   const int64_t warps = (int64_t)n_mol * n_out;
   if (n_nodes == 0 || warps == 0) return 0;
   atomwise_reduce_bwd_kernel<<<(unsigned)cdiv64(warps * 32, 256), 256, 0, st>>>(g_y, g_yi, stddev, n_stat, mol_ptr, n_mol,

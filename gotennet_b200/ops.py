@@ -303,11 +303,10 @@ class EdgeGeometryFn(torch.autograd.Function):
         g_Y = g_Y.contiguous() if g_Y is not None else None
         g_fc = g_fc.contiguous() if g_fc is not None else None
         g_phi = g_phi.contiguous() if g_phi is not None else None
+        g_r = g_r.contiguous() if g_r is not None else None   # d|v|/dv = u is applied inside the kernel (loops: 0)
         lib().call("goten_edge_geometry_bwd", _ptr(r), _ptr(u), _ptr(plan.src), _ptr(plan.tgt), E, ctx.lmax,
                    ctx.cutoff, means.numel(), ctx.basis, _ptr(means), _ptr(betas), _ptr(g_phi), _ptr(g_fc), _ptr(g_Y),
-                   _ptr(g_vec), _stream())
-        if g_r is not None:
-            g_vec = g_vec + g_r.unsqueeze(-1) * u  # d|v|/dv = u (self loops: u = 0)
+                   _ptr(g_r), _ptr(g_vec), _stream())
         if ctx.from_pos:
             g_pos = torch.empty(ctx.n_pos, 3, device=r.device)
             lib().call("goten_edge_vec_to_pos_bwd", _ptr(g_vec), _ptr(plan.tgt_ptr), _ptr(plan.src_ptr),
@@ -648,7 +647,10 @@ class GataBlockFn(torch.autograd.Function):
                      add_src=g_Xd1, ld_add=C, add_off=off, am=am)
                 gemm(g_EQK, 2 * C, 1, Xd1, C, 0, dWqk, C, 2 * C, C, rows, a_off=2 * off, b_off=off,
                      c_off=g * 2 * C * C, am=am)
-            dWvq = dWqk[:, :C].sum(0) if G > 1 else dWqk[0, :C].contiguous()
+            # W_vq is shared by the degree groups: its gradient is the sum of the groups' [C, C] blocks (goten_add)
+            dWvq = dWqk[0, :C].contiguous()
+            for g in range(1, G):
+                L_.call("goten_add", _ptr(dWvq), _ptr(dWqk, g * 2 * C * C), _ptr(dWvq), C * C, st)
             dWvk = dWqk[:, C:].contiguous()
         # message block
         g_Z1 = torch.empty(N, 4 * C, device=dev)
@@ -839,11 +841,6 @@ class AtomwiseReduceFn(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, g_yi, g_y):
         stddev, mol_ptr = ctx.saved_tensors
-        if ctx.mode == 0:
-            g = g_yi if g_y is None else (g_y if g_yi is None else g_yi + g_y)
-            if stddev is not None:
-                g = g * stddev
-            return g, None, None, None, None, None, None, None
         ref = g_yi if g_yi is not None else g_y
         N = ctx.N
         n_out = ref.shape[1]

@@ -95,7 +95,7 @@ int goten_edge_geometry_fwd(const float* pos, const float* edge_vec_in, const fl
 int goten_edge_geometry_bwd(const float* r, const float* u, const int32_t* src, const int32_t* tgt,
                             int64_t n_edges, int lmax, float cutoff, int n_rbf, int basis,
                             const float* means, const float* betas, const float* g_phi, const float* g_fc,
-                            const float* g_Y, float* g_vec, void* stream);
+                            const float* g_Y, const float* g_r, float* g_vec, void* stream);
 /* scatter of per-edge vector gradients onto positions: g_pos[i] = sum_{e: src=i} g - sum_{e: tgt=i} g */
 int goten_edge_vec_to_pos_bwd(const float* g_vec, const int32_t* tgt_ptr, const int32_t* src_ptr,
                               const int32_t* src_perm, int n_nodes, float* g_pos, void* stream);
