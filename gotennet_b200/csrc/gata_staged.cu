@@ -15,6 +15,7 @@
 // No atomics: results are bit-reproducible run to run.
 #include "common.cuh"
 #include "tma.cuh"
+#include "umma.cuh"   // tensor-map TMA (cp.async.bulk.tensor) + cuTensorMapEncodeTiled entry point
 
 namespace goten {
 
@@ -104,22 +105,29 @@ __global__ void gata_attn_fwd_kernel(const float* __restrict__ qk, int ldqk, con
 }
 
 // ------------------------------------------------------------- messages -------
-// Stage layout (floats): filter Ze[e, C:(S+1)C] [S*C] | x_j [S*C] | v_j [S*C] | X_j [L*C]
+// CTA = (target i, channel slice sl of CH = C / n_slices channels).  Stage layout (floats, this slice only):
+//   filter Ze[e, C + k*C + sl*CH ..] [S][CH] | x_j [S][CH] | v_j [S][CH] | X_j [L][CH]
+// Each of the four pieces arrives by ONE tensor-map TMA copy (3-D boxes over Ze viewed as [E][ldz/C][C], x / v as
+// [N][S][C], Xd as [L][N][C]), so a stage costs four issued instructions whatever S and L are, and a slice of half the
+// channels halves the stage (n_slices(), measured neutral: the kernels are bound by bytes in flight per SM - ring depth 2
+// instead of 1 costs 40 % - and a half-width CTA keeps half the bytes in flight).
 template <int LMAX, bool SD, bool ST>
-__global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __restrict__ Xd, const float* __restrict__ x,
-                                    const float* __restrict__ v, const float* __restrict__ Ze, int ldz,
+__global__ void gata_msg_fwd_kernel(const __grid_constant__ CUtensorMap tmZe, const __grid_constant__ CUtensorMap tmX,
+                                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmXd,
+                                    const float* __restrict__ h, const float* __restrict__ Xd,
                                     const float* __restrict__ Y, const float* __restrict__ fc,
                                     const float* __restrict__ kappa, const float* __restrict__ drop, const float* __restrict__ alpha,
                                     const int32_t* __restrict__ tgt_ptr, const int32_t* __restrict__ src, int N, int C,
-                                    int H, int R, float* __restrict__ h_out, float* __restrict__ Xd_out,
+                                    int CH, int H, int R, float* __restrict__ h_out, float* __restrict__ Xd_out,
                                     float* __restrict__ xd_amax) {
   using Cf = Cfg<LMAX, SD, ST>;
   constexpr int L = Cf::L, S = Cf::S, ND = Cf::ND;
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const int tid = threadIdx.x, c = tid * 4, C4 = C >> 2;
-  const bool act = c < C;
-  const int SC = S * C;
-  const int stage_floats = (3 * S + L) * C;
+  const int tid = threadIdx.x, CH4 = CH >> 2;
+  const int c0s = blockIdx.y * CH;            // first channel of this slice
+  const int c = c0s + tid * 4;
+  const bool act = tid * 4 < CH;
+  const int stage_floats = (3 * S + L) * CH;
   const uint32_t stage_bytes = (uint32_t)stage_floats * 4u;
   float* stages = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)R * stage_bytes);
@@ -146,17 +154,16 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
 #pragma unroll
   for (int m = 0; m < L; ++m) accX[m] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  auto issue = [&](int gt, int t_local) {  // elected thread: all rows of edge gt -> stage gt % R
+  auto issue = [&](int gt, int t_local) {  // elected thread: the four boxes of edge gt -> stage gt % R
     const int s = gt % R;
     const uint32_t bar = bar0 + 8 * s, dst = stage0 + (uint32_t)s * stage_bytes;
     const int j = s_src[t_local];
+    const uint32_t piece = (uint32_t)(S * CH) * 4u;
     tma::mbar_expect_tx(bar, stage_bytes);
-    tma::bulk_g2s(dst, Ze + (size_t)(e0 + gt) * ldz + C, (uint32_t)SC * 4u, bar);
-    tma::bulk_g2s(dst + (uint32_t)SC * 4u, x + (size_t)j * SC, (uint32_t)SC * 4u, bar);
-    tma::bulk_g2s(dst + 2u * (uint32_t)SC * 4u, v + (size_t)j * SC, (uint32_t)SC * 4u, bar);
-#pragma unroll
-    for (int m = 0; m < L; ++m)
-      tma::bulk_g2s(dst + (3u * (uint32_t)SC + (uint32_t)(m * C)) * 4u, Xd + ((size_t)m * N + j) * C, (uint32_t)C * 4u, bar);
+    tc::tma_load_3d(dst, &tmZe, bar, c0s, 1, e0 + gt);            // chunks 1 .. S of the edge's projection row
+    tc::tma_load_3d(dst + piece, &tmX, bar, c0s, 0, j);
+    tc::tma_load_3d(dst + 2u * piece, &tmV, bar, c0s, 0, j);
+    tc::tma_load_3d(dst + 3u * piece, &tmXd, bar, c0s, j, 0);     // the L degree rows of node j
   };
 
   for (int c0 = 0; c0 < deg; c0 += EC) {
@@ -185,7 +192,7 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
         float4 o[S];
 #pragma unroll
         for (int k = 0; k < S; ++k) {
-          const float4 tf = st[k * C4 + tid], xv = st[(S + k) * C4 + tid], vv = st[(2 * S + k) * C4 + tid];
+          const float4 tf = st[k * CH4 + tid], xv = st[(S + k) * CH4 + tid], vv = st[(2 * S + k) * CH4 + tid];
           const float al = s_al[t * H + hd_of[k]] * kap;
           o[k] = make_float4(tf.x * xv.x * f + al * vv.x, tf.y * xv.y * f + al * vv.y, tf.z * xv.z * f + al * vv.z,
                              tf.w * xv.w * f + al * vv.w);
@@ -195,7 +202,7 @@ __global__ void gata_msg_fwd_kernel(const float* __restrict__ h, const float* __
         for (int l = 0; l < LMAX; ++l) {
 #pragma unroll
           for (int m = lo_of(l); m < hi_of(l); ++m) {
-            const float4 Xj = st[(3 * S) * C4 + m * C4 + tid];
+            const float4 Xj = st[(3 * S) * CH4 + m * CH4 + tid];
             const float y = s_Y[t * L + m];
             const float4 od = o[1 + (SD ? l : 0)], ot = o[1 + ND + (ST ? l : 0)];
             accX[m].x += y * od.x + Xj.x * ot.x;
@@ -663,6 +670,31 @@ __global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const 
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// channel slices per node CTA.  Default 1: halving the slice (twice the CTAs, half the stage each) was measured
+// neutral-to-slower on B200 (cfg2 forward 2.65 -> 2.79 ms): bytes in flight per SM stay the same and the per-edge
+// barrier / issue cost doubles.  GOTEN_GATA_SLICES=2 selects halves of >= 128 channels for experiments.
+static int n_slices(int C) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("GOTEN_GATA_SLICES"); env = e ? atoi(e) : 0; }
+  int n = env > 0 ? env : 1;
+  while (n > 1 && (C % n != 0 || (C / n) % 128 != 0)) --n;
+  return n < 1 ? 1 : n;
+}
+
+// 3-D fp32 tensor map over P with extents (d0, d1, d2) (d0 contiguous), byte strides (s1, s2), box (b0, b1, b2), no swizzle
+static bool map3d(CUtensorMap* m, const float* P, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2,
+                  uint32_t b0, uint32_t b1, uint32_t b2) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1, s2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(P), dims, strides, box, es,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int ring_depth() {
   static int r = 0;
   if (r == 0) {
@@ -725,13 +757,27 @@ int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, 
   if (max_deg_in < 1) max_deg_in = 1;
   const size_t smem_a = (size_t)max_deg_in * (nparts + H) * sizeof(float);
   if (smem_a > 200 * 1024) return 0;
-  // message kernel: ring of R stages + mbarriers + per-chunk scalars
+  // message kernel: CTAs = (target, channel slice); ring of R stages + mbarriers + per-chunk scalars
+  const int nsl = staged::n_slices(C);
+  const int CH = C / nsl;
+  if (ldz % C != 0 || get_encode() == nullptr) return 0;
   int R = staged::ring_depth();
-  const size_t stage_bytes = (size_t)(3 * S + L) * C * 4;
+  const size_t stage_bytes = (size_t)(3 * S + L) * CH * 4;
   const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (3 + L + H) * 4;
   while (R > 1 && R * stage_bytes + tail > 220 * 1024) --R;
   const size_t smem_m = R * stage_bytes + tail;
   if (smem_m > 220 * 1024) return 0;
+  CUtensorMap mZe, mX, mV, mXd;
+  {
+    const int SC = S * C;
+    // the host does not know E here: N * max in-degree bounds it (the map's outer extent only guards out-of-range boxes)
+    const uint64_t e_bound = (uint64_t)N * (uint64_t)max_deg_in;
+    const bool ok = staged::map3d(&mZe, Ze, C, ldz / C, e_bound, (uint64_t)C * 4, (uint64_t)ldz * 4, CH, S, 1) &&
+                    staged::map3d(&mX, x, C, S, N, (uint64_t)C * 4, (uint64_t)SC * 4, CH, S, 1) &&
+                    staged::map3d(&mV, v, C, S, N, (uint64_t)C * 4, (uint64_t)SC * 4, CH, S, 1) &&
+                    staged::map3d(&mXd, Xd, C, N, L, (uint64_t)C * 4, (uint64_t)N * C * 4, CH, 1, L);
+    GOTEN_REQUIRE(ok, "cuTensorMapEncodeTiled failed (GATA message kernel, N=%d C=%d ldz=%d)", N, C, ldz);
+  }
   {
     auto kfn = staged::gata_attn_fwd_kernel;
     if (smem_a > 48 * 1024)
@@ -739,8 +785,9 @@ int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, 
     kfn<<<N, block, smem_a, st>>>(qk, ldqk, Ze, ldz, tgt_ptr, src, C, H, max_deg_in, alpha);
     GOTEN_CHECK_LAUNCH();
   }
-  STAGED_DISPATCH(gata_msg_fwd_kernel, N, block, smem_m, h, Xd, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, tgt_ptr, src, N, C, H,
-                  R, h_out, Xd_out, xd_amax);
+  const int block_m = ((CH / 4 + 31) / 32) * 32;
+  STAGED_DISPATCH(gata_msg_fwd_kernel, dim3((unsigned)N, (unsigned)nsl), block_m, smem_m, mZe, mX, mV, mXd, h, Xd, Y, fc, kappa,
+                  drop, alpha, tgt_ptr, src, N, C, CH, H, R, h_out, Xd_out, xd_amax);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
   return 0;
