@@ -241,7 +241,7 @@ __global__ void gata_msg_fwd_kernel(const __grid_constant__ CUtensorMap tmZe, co
 // filter row of the edge is read straight from Ze (it is used once, by one thread).
 template <int LMAX, bool SD, bool ST, bool GEO>
 __device__ __forceinline__ void gata_bwd_tgt_staged_body(
-    const float* __restrict__ g_h, const float* __restrict__ g_Xd, const float* __restrict__ Xd,
+    const CUtensorMap& tmXd, const float* __restrict__ g_h, const float* __restrict__ g_Xd, const float* __restrict__ Xd,
     const float* __restrict__ qk, int ldqk, const float* __restrict__ x, const float* __restrict__ v,
     const float* __restrict__ Ze, int ldz, const float* __restrict__ Y, const float* __restrict__ fc,
     const float* __restrict__ kappa, const float* __restrict__ drop, const float* __restrict__ alpha, const int32_t* __restrict__ tgt_ptr,
@@ -301,9 +301,7 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
     const uint32_t bar = bar0 + 8 * s, dst = stage0 + (uint32_t)s * stage_bytes;
     const int j = s_src[t_local];
     tma::mbar_expect_tx(bar, stage_bytes);
-#pragma unroll
-    for (int m = 0; m < L; ++m)
-      tma::bulk_g2s(dst + (uint32_t)(m * C) * 4u, Xd + ((size_t)m * N + j) * C, (uint32_t)C * 4u, bar);
+    tc::tma_load_3d(dst, &tmXd, bar, 0, j, 0);   // the L degree rows of node j in one tensor-map copy
     tma::bulk_g2s(dst + (uint32_t)(L * C) * 4u, v + (size_t)j * SC, (uint32_t)SC * 4u, bar);
     tma::bulk_g2s(dst + (uint32_t)(L * C + SC) * 4u, x + (size_t)j * SC, (uint32_t)SC * 4u, bar);
   };
@@ -484,7 +482,7 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
 }
 
 #define GOTEN_BWD_TGT_ARGS                                                                                            \
-  const float *__restrict__ g_h, const float *__restrict__ g_Xd, const float *__restrict__ Xd,                       \
+  const __grid_constant__ CUtensorMap tmXd, const float *__restrict__ g_h, const float *__restrict__ g_Xd, const float *__restrict__ Xd,                       \
       const float *__restrict__ qk, int ldqk, const float *__restrict__ x, const float *__restrict__ v,              \
       const float *__restrict__ Ze, int ldz, const float *__restrict__ Y, const float *__restrict__ fc,              \
       const float *__restrict__ kappa, const float *__restrict__ drop, const float *__restrict__ alpha, const int32_t *__restrict__ tgt_ptr,         \
@@ -492,7 +490,7 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
       int ldgqk, float *__restrict__ gZe, int ldgz, float *__restrict__ da_out, float *__restrict__ gze_amax,        \
       float *__restrict__ g_fc, float *__restrict__ g_Y
 #define GOTEN_BWD_TGT_PASS                                                                                          \
-  g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, tgt_ptr, src, N, C, H, R, max_deg, g_cols, g_qk, ldgqk, \
+  tmXd, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha, tgt_ptr, src, N, C, H, R, max_deg, g_cols, g_qk, ldgqk, \
       gZe, ldgz, da_out, gze_amax, g_fc, g_Y
 template <int LMAX, bool SD, bool ST>
 __global__ void gata_bwd_tgt_staged_kernel(GOTEN_BWD_TGT_ARGS) {
@@ -510,7 +508,8 @@ __global__ void gata_bwd_tgt_staged_geo_kernel(GOTEN_BWD_TGT_ARGS) {
 //   Ze[e, 0:(S+1)C] [(S+1)*C] | g_h_i [C] | g_Xd_i [L*C] | q_i [C]
 // Own rows (X_j, and the tensor chunks of x_j / v_j) sit in shared memory; dx_j, dv_j, dk_j, dX_j accumulate in registers.
 template <int LMAX, bool SD, bool ST>
-__global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const float* __restrict__ g_Xd,
+__global__ void gata_bwd_src_staged_kernel(const __grid_constant__ CUtensorMap tmGX, const float* __restrict__ g_h,
+                                           const float* __restrict__ g_Xd,
                                            const float* __restrict__ Xd, const float* __restrict__ qk, int ldqk,
                                            const float* __restrict__ x, const float* __restrict__ v,
                                            const float* __restrict__ Ze, int ldz, const float* __restrict__ Y,
@@ -574,9 +573,7 @@ __global__ void gata_bwd_src_staged_kernel(const float* __restrict__ g_h, const 
     tma::mbar_expect_tx(bar, stage_bytes);
     tma::bulk_g2s(dst, Ze + (size_t)e * ldz, (uint32_t)(S + 1) * (uint32_t)C * 4u, bar);
     tma::bulk_g2s(dst + (uint32_t)((S + 1) * C) * 4u, g_h + (size_t)i * C, (uint32_t)C * 4u, bar);
-#pragma unroll
-    for (int m = 0; m < L; ++m)
-      tma::bulk_g2s(dst + (uint32_t)((S + 2 + m) * C) * 4u, g_Xd + ((size_t)m * N + i) * C, (uint32_t)C * 4u, bar);
+    tc::tma_load_3d(dst + (uint32_t)((S + 2) * C) * 4u, &tmGX, bar, 0, i, 0);   // the L rows of g_Xd_i in one copy
     tma::bulk_g2s(dst + (uint32_t)((S + 2 + L) * C) * 4u, qk + (size_t)i * ldqk, (uint32_t)C * 4u, bar);
   };
 
@@ -760,7 +757,7 @@ int gata_fwd_staged(const float* h, const float* Xd, const float* qk, int ldqk, 
   // message kernel: CTAs = (target, channel slice); ring of R stages + mbarriers + per-chunk scalars
   const int nsl = staged::n_slices(C);
   const int CH = C / nsl;
-  if (ldz % C != 0 || get_encode() == nullptr) return 0;
+  if (ldz % C != 0 || CH > 256 || get_encode() == nullptr) return 0;   // (a TMA box holds <= 256 elements per dim)
   int R = staged::ring_depth();
   const size_t stage_bytes = (size_t)(3 * S + L) * CH * 4;
   const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (3 + L + H) * 4;
@@ -822,11 +819,15 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   while (R > 1 && R * stage_bytes + tail > 220 * 1024) --R;
   const size_t smem = R * stage_bytes + tail;
   if (R * stage_bytes + tail > 220 * 1024) return 0;
+  if (C > 256 || get_encode() == nullptr) return 0;   // (a TMA box holds at most 256 elements per dimension)
+  CUtensorMap mXd;
+  GOTEN_REQUIRE(staged::map3d(&mXd, Xd, C, N, L, (uint64_t)C * 4, (uint64_t)N * C * 4, C, 1, L),
+                "cuTensorMapEncodeTiled failed (GATA backward, N=%d C=%d)", N, C);
   if (geo)
-    STAGED_DISPATCH(gata_bwd_tgt_staged_geo_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop,
+    STAGED_DISPATCH(gata_bwd_tgt_staged_geo_kernel, N, block, smem, mXd, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop,
                     alpha, tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y);
   else
-    STAGED_DISPATCH(gata_bwd_tgt_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha,
+    STAGED_DISPATCH(gata_bwd_tgt_staged_kernel, N, block, smem, mXd, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha,
                     tgt_ptr, src, N, C, H, R, max_deg_in, g_cols, g_qk, ldgqk, gZe, ldgz, da, gze_amax, g_fc, g_Y);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
@@ -855,7 +856,11 @@ int gata_bwd_src_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   while (R > 1 && R * stage_bytes + tail > 220 * 1024) --R;
   if (R * stage_bytes + tail > 220 * 1024) return 0;
   const size_t smem = R * stage_bytes + tail;
-  STAGED_DISPATCH(gata_bwd_src_staged_kernel, N, block, smem, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha,
+  if (C > 256 || get_encode() == nullptr) return 0;   // (a TMA box holds at most 256 elements per dimension)
+  CUtensorMap mGX;
+  GOTEN_REQUIRE(staged::map3d(&mGX, g_Xd, C, N, L, (uint64_t)C * 4, (uint64_t)N * C * 4, C, 1, L),
+                "cuTensorMapEncodeTiled failed (GATA backward, N=%d C=%d)", N, C);
+  STAGED_DISPATCH(gata_bwd_src_staged_kernel, N, block, smem, mGX, g_h, g_Xd, Xd, qk, ldqk, x, v, Ze, ldz, Y, fc, kappa, drop, alpha,
                   da, src_ptr, src_perm, tgt, N, C, H, R, g_qk, ldgqk, g_x, g_v, g_Xd_in, gx_amax, gv_amax);
   GOTEN_CHECK_LAUNCH();
   *handled = true;
