@@ -278,7 +278,8 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
   const int deg = tgt_ptr[i + 1] - e0;
   if (deg > max_deg) __trap();
   if (tid == 0) {
-    for (int s = 0; s < R; ++s) tma::mbar_init(bar0 + 8 * s, 1);
+    tma::mbar_init(bar0, 1);
+    tma::mbar_init(bar0 + 8, 1);
     tma::fence_barrier_init();
   }
   int hd_of[S];
@@ -296,14 +297,20 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
     for (int m = 0; m < L; ++m) gX[m] = ld4(g_Xd + ((size_t)m * N + i) * C + c);
   }
 
-  auto issue = [&](int gt, int t_local) {
-    const int s = gt % R;
-    const uint32_t bar = bar0 + 8 * s, dst = stage0 + (uint32_t)s * stage_bytes;
+  // ONE stage, refilled in two pieces with their own barriers (slots 0 / 1): piece X = the L rows of X_j, consumed by the
+  // first half of an edge's work (dout), piece VX = v_j | x_j, consumed by the second half.  As soon as every thread is
+  // past the first half, the next edge's X piece is requested, so its round trip overlaps the second half - the overlap
+  // of a deeper ring without its shared memory (ring depth 2 halves the resident CTAs: +40 %).  (R is unused here.)
+  const uint32_t barX = bar0, barV = bar0 + 8;
+  auto issueX = [&](int t_local) {
+    tma::mbar_expect_tx(barX, (uint32_t)(L * C) * 4u);
+    tc::tma_load_3d(stage0, &tmXd, barX, 0, s_src[t_local], 0);   // the L degree rows of node j in one tensor-map copy
+  };
+  auto issueV = [&](int t_local) {
     const int j = s_src[t_local];
-    tma::mbar_expect_tx(bar, stage_bytes);
-    tc::tma_load_3d(dst, &tmXd, bar, 0, j, 0);   // the L degree rows of node j in one tensor-map copy
-    tma::bulk_g2s(dst + (uint32_t)(L * C) * 4u, v + (size_t)j * SC, (uint32_t)SC * 4u, bar);
-    tma::bulk_g2s(dst + (uint32_t)(L * C + SC) * 4u, x + (size_t)j * SC, (uint32_t)SC * 4u, bar);
+    tma::mbar_expect_tx(barV, 2u * (uint32_t)SC * 4u);
+    tma::bulk_g2s(stage0 + (uint32_t)(L * C) * 4u, v + (size_t)j * SC, (uint32_t)SC * 4u, barV);
+    tma::bulk_g2s(stage0 + (uint32_t)(L * C + SC) * 4u, x + (size_t)j * SC, (uint32_t)SC * 4u, barV);
   };
 
   // ---- pass A
@@ -313,26 +320,23 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
     for (int t = tid; t < n; t += blockDim.x) { s_src[t] = src[e0 + c0 + t]; s_fc[t] = fc[e0 + c0 + t]; }
     for (int t = tid; t < n * L; t += blockDim.x) s_Y[t] = Y[(size_t)(e0 + c0) * L + t];
     __syncthreads();
-    if (tid == 0) {
-      const int pre = n < R ? n : R;
-      for (int u = 0; u < pre; ++u) issue(c0 + u, u);
-    }
+    if (tid == 0) { issueX(0); issueV(0); }
     for (int t = 0; t < n; ++t) {
-      const int gt = c0 + t, s = gt % R;
+      const int gt = c0 + t;
+      constexpr int s = 0;
       float pk[S];
 #pragma unroll
       for (int k = 0; k < S; ++k) pk[k] = 0.f;
       float geo[1 + L];  // GEO: [d fc | d Y_m] partials of this thread
 #pragma unroll
       for (int m = 0; m <= L; ++m) geo[m] = 0.f;
-      if (act) {
-        tma::mbar_wait(bar0 + 8 * s, (uint32_t)((gt / R) & 1));
-        const float4* st = reinterpret_cast<const float4*>(stages + (size_t)s * stage_floats);
-        const float f = s_fc[t];
-        float4 dout[S];
-        dout[0] = gh;
+      const float4* st = reinterpret_cast<const float4*>(stages + (size_t)s * stage_floats);
+      float4 dout[S];
+      dout[0] = gh;
 #pragma unroll
-        for (int k = 1; k < S; ++k) dout[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 1; k < S; ++k) dout[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (act) {
+        tma::mbar_wait(barX, (uint32_t)(gt & 1));
 #pragma unroll
         for (int l = 0; l < LMAX; ++l) {
 #pragma unroll
@@ -343,6 +347,12 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
             dout[1 + ND + (ST ? l : 0)] = fma44(Xj, gX[m], dout[1 + ND + (ST ? l : 0)]);
           }
         }
+      }
+      __syncthreads();                                   // every thread is past the X piece
+      if (tid == 0 && t + 1 < n) issueX(t + 1);
+      if (act) {
+        tma::mbar_wait(barV, (uint32_t)(gt & 1));
+        const float f = s_fc[t];
         float* gz = gZe + (size_t)(e0 + gt) * ldgz + C + c;
         float4 od[ND];  // GEO: forward messages of the direction chunks (gotennet.py:522-526, 532)
         const float kap = GEO ? kappa[e0 + gt] : 0.f;
@@ -406,7 +416,7 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
         }
         part[(size_t)t * S * n_grp + o] = p;
       }
-      if (tid == 0 && t + R < n) issue(gt + R, t + R);
+      if (tid == 0 && t + 1 < n) issueV(t + 1);           // (after the barrier above: everybody is past v_j | x_j)
     }
     // ---- chunk epilogue: d alpha~[e][hd] = kappa_e * sum of the group sums whose columns lie in head hd
     // (per chunk, so `part` holds EC edges whatever the in-degree: 160-neighbour molecules keep 4 CTAs per SM)
@@ -811,7 +821,7 @@ int gata_bwd_tgt_staged(const float* g_h, const float* g_Xd, const float* Xd, co
   const int block = ((C / 4 + 31) / 32) * 32;
   if (block > 1024) return 0;
   if (max_deg_in < 1) max_deg_in = 1;
-  int R = staged::ring_depth();
+  int R = 1;   // one stage, refilled in two pieces (see the kernel)
   const size_t stage_bytes = (size_t)(2 * S + L) * C * 4;
   const bool geo = g_fc != nullptr || g_Y != nullptr;
   const size_t tail = (size_t)8 * 8 + (size_t)staged::EC * (2 + L + S * n_grp) * 4 + (size_t)max_deg_in * 2 * H * 4 +
