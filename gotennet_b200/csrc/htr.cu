@@ -19,6 +19,10 @@ constexpr int HTR_SEP = 1, HTR_REJ = 2;
 __device__ __forceinline__ int htr_gate(int flags) { return (flags >> 2) & 3; }
 // bit 4: gamma_t ends without an activation ("mlp" variant, gotennet.py:244-248): zt is used as is instead of SiLU(zt)
 constexpr int HTR_T_LINEAR = 16;
+// bit 5: emit / differentiate the raw weight w only (the "linw" family, gotennet.py:270-282: gamma_w is then a small
+// network on w[E][evec_dim], run by the host as LayerNorm / activation / GEMM launches).  Forward: t_out[e][c] = w;
+// backward: g_t_out IS dL/dw, no gZe is produced; Ze / t are not read.  C is then evec_dim.
+constexpr int HTR_W_ONLY = 32;
 __device__ __forceinline__ float gate_f(float w, int gate) {
   if (gate == 1) return sigmoidf_(w);
   if (gate == 2) return tanhf(w);
@@ -214,8 +218,11 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
     float k[L][V], y[L], zt[V], tv[V];
 #pragma unroll
     for (int m = 0; m < L; ++m) { ldv<V>(EK + ((size_t)m * N + j) * ldp + c, k[m]); y[m] = Y[(size_t)e * L + m]; }
-    ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
-    ldv<V>(t + (size_t)e * C + c, tv);
+    const bool w_only = GATED && (flags & HTR_W_ONLY);
+    if (!w_only) {
+      ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
+      ldv<V>(t + (size_t)e * C + c, tv);
+    }
     float nn[3];
     htr_coef<LMAX>(y, flags, nn);
 #pragma unroll
@@ -223,8 +230,13 @@ __global__ void htr_fwd_kernel(const float* __restrict__ EQ, const float* __rest
       float qc[L], kc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(k, qq, kc);
-      const float gt_ = (GATED && (flags & HTR_T_LINEAR)) ? zt[qq] : siluf_(zt[qq]);
-      tv[qq] = fmaf(gt_, gate_f(htr_weight<LMAX>(qc, kc, y, nn, flags), gate), tv[qq]);
+      const float w = htr_weight<LMAX>(qc, kc, y, nn, flags);
+      if (w_only) {
+        tv[qq] = w;
+      } else {
+        const float gt_ = (GATED && (flags & HTR_T_LINEAR)) ? zt[qq] : siluf_(zt[qq]);
+        tv[qq] = fmaf(gt_, gate_f(w, gate), tv[qq]);
+      }
       amx = fmaxf(amx, fabsf(tv[qq]));
     }
     stv<V>(t_out + (size_t)e * C + c, tv);
@@ -270,7 +282,8 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
         float k[L][V], zt[V], dt[V], gz[V];
 #pragma unroll
         for (int m = 0; m < L; ++m) ldv<V>(EK + ((size_t)m * N + j) * ldp + c, k[m]);
-        ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
+        const bool w_only = GATED && (flags & HTR_W_ONLY);
+        if (!w_only) ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
         ldv<V>(g_t_out + (size_t)e * C + c, dt);
         const float nn[3] = {sm.n[u * 3], sm.n[u * 3 + 1], sm.n[u * 3 + 2]};
 #pragma unroll
@@ -279,6 +292,12 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
           col_of<L, V>(q, qq, qc);
           col_of<L, V>(k, qq, kc);
           col_of<L, V>(gq, qq, gc);
+          if (w_only) {  // dt is dL/dw
+            htr_weight_grad<LMAX, GY>(qc, kc, y, nn, flags, dt[qq], gc, gy);
+#pragma unroll
+            for (int m = 0; m < L; ++m) gq[m][qq] = gc[m];
+            continue;
+          }
           const bool t_lin = GATED && (flags & HTR_T_LINEAR);
           const float sg = sigmoid_fast_(zt[qq]);
           float dw = t_lin ? dt[qq] * zt[qq] : dt[qq] * zt[qq] * sg;              // dt * gamma_t: zt or silu(zt)
@@ -290,7 +309,7 @@ __device__ __forceinline__ void htr_bwd_tgt_body(const float* __restrict__ g_t_o
 #pragma unroll
           for (int m = 0; m < L; ++m) gq[m][qq] = gc[m];
         }
-        stv<V>(gZe + (size_t)e * ldgz + zt_col0 + c, gz);
+        if (!w_only) stv<V>(gZe + (size_t)e * ldgz + zt_col0 + c, gz);
       }
       if (GY) {  // geometry gradient for forces (block-uniform): L channel sums, one barrier
         block_sums_one_barrier<L>(gy, gy_scratch + (size_t)(u & 1) * L * (blockDim.x + 4),
@@ -360,7 +379,8 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
     float q[L][V], y[L], zt[V], dt[V];
 #pragma unroll
     for (int m = 0; m < L; ++m) { ldv<V>(EQ + ((size_t)m * N + i) * ldp + c, q[m]); y[m] = Y[(size_t)e * L + m]; }
-    ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
+    const bool w_only = GATED && (flags & HTR_W_ONLY);
+    if (!w_only) ldv<V>(Ze + (size_t)e * ldz + zt_col0 + c, zt);
     ldv<V>(g_t_out + (size_t)e * C + c, dt);
     float nn[3];
     htr_coef<LMAX>(y, flags, nn);
@@ -369,7 +389,8 @@ __global__ void htr_bwd_src_kernel(const float* __restrict__ g_t_out, const floa
       float qc[L], gc[L];
       col_of<L, V>(q, qq, qc);
       col_of<L, V>(gk, qq, gc);
-      float dw = (GATED && (flags & HTR_T_LINEAR)) ? dt[qq] * zt[qq] : dt[qq] * silu_fast_(zt[qq]);
+      float dw = w_only ? dt[qq]
+                        : ((GATED && (flags & HTR_T_LINEAR)) ? dt[qq] * zt[qq] : dt[qq] * silu_fast_(zt[qq]));
       if (gate) {
         float kc[L];
         col_of<L, V>(kown, qq, kc);
@@ -407,7 +428,7 @@ using namespace goten;
 
 #define HTR_LAUNCH(KERNEL, LM, VV, T, ...)                                                      \
   do {                                                                                         \
-    if ((flags >> 2) & 7) KERNEL<LM, VV, true><<<N, T, 0, st>>>(__VA_ARGS__);                  \
+    if ((flags >> 2) & 15) KERNEL<LM, VV, true><<<N, T, 0, st>>>(__VA_ARGS__);                  \
     else KERNEL<LM, VV, false><<<N, T, 0, st>>>(__VA_ARGS__);                                  \
   } while (0)
 

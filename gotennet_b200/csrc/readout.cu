@@ -99,20 +99,49 @@ __global__ void atomwise_scale_bwd_kernel(const float* __restrict__ g_y, const f
   g_raw[idx] = g * (stddev ? stddev[n_stat > 1 ? o : 0] : 1.f);
 }
 
-// element-wise activations of the head MLP: kind 1 = SiLU, 2 = shifted softplus ln(1 + e^x) - ln 2
+// element-wise activations (head MLP; gamma_w of the "linw" edge updates): kind 1 = SiLU, 2 = shifted softplus
+// ln(1 + e^x) - ln 2, 3 = sigmoid, 4 = tanh
 __device__ __forceinline__ float softplusf_(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // torch threshold = 20
+__device__ __forceinline__ float act_value(int kind, float v) {
+  if (kind == 1) return siluf_(v);
+  if (kind == 2) return softplusf_(v) - 0.69314718055994530942f;
+  if (kind == 3) return sigmoidf_(v);
+  return tanhf(v);
+}
+__device__ __forceinline__ float act_slope(int kind, float v) {
+  if (kind == 1) return dsiluf_(v);
+  if (kind == 2) return v > 20.f ? 1.f : sigmoidf_(v);
+  if (kind == 3) { const float s = sigmoidf_(v); return s * (1.0f - s); }
+  const float t = tanhf(v);
+  return 1.0f - t * t;
+}
 __global__ void act_fwd_kernel(int kind, const float* __restrict__ x, int64_t n, float* __restrict__ y) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float v = x[i];
-  y[i] = kind == 1 ? siluf_(v) : softplusf_(v) - 0.69314718055994530942f;
+  y[i] = act_value(kind, x[i]);
 }
 __global__ void act_bwd_kernel(int kind, const float* __restrict__ g, const float* __restrict__ x, int64_t n,
                                float* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const float v = x[i];
-  out[i] = g[i] * (kind == 1 ? dsiluf_(v) : (v > 20.f ? 1.f : sigmoidf_(v)));
+  out[i] = g[i] * act_slope(kind, x[i]);
+}
+
+// t' = a * b + c and its gradients g_a = g * b, g_b = g * a (g_c = g): the residual edge update
+// t_ij + gamma_t(t_ij) * gamma_w(w_ij) (gotennet.py:611, :445) when gamma_w is a host-composed network
+__global__ void mul_add_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                   int64_t n, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[i] = fmaf(a[i], b[i], c[i]);
+}
+__global__ void mul_add_bwd_kernel(const float* __restrict__ g, const float* __restrict__ a, const float* __restrict__ b,
+                                   int64_t n, float* __restrict__ g_a, float* __restrict__ g_b) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float gi = g[i];
+  g_a[i] = gi * b[i];
+  g_b[i] = gi * a[i];
 }
 
 }  // namespace goten
@@ -180,7 +209,7 @@ int goten_atomwise_reduce_bwd(const float* g_y, const float* g_yi, const float* 
 }
 
 int goten_act_fwd(int kind, const float* x, int64_t n, float* y, void* stream) {
-  GOTEN_REQUIRE(kind == 1 || kind == 2, "activation kind %d unsupported (1 silu, 2 shifted softplus)", kind);
+  GOTEN_REQUIRE(kind >= 1 && kind <= 4, "activation kind %d unsupported (1 silu, 2 shifted softplus, 3 sigmoid, 4 tanh)", kind);
   if (n == 0) return 0;
   act_fwd_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, as_stream(stream)>>>(kind, x, n, y);
   GOTEN_CHECK_LAUNCH();
@@ -188,9 +217,23 @@ int goten_act_fwd(int kind, const float* x, int64_t n, float* y, void* stream) {
 }
 
 int goten_act_bwd(int kind, const float* g, const float* x, int64_t n, float* out, void* stream) {
-  GOTEN_REQUIRE(kind == 1 || kind == 2, "activation kind %d unsupported (1 silu, 2 shifted softplus)", kind);
+  GOTEN_REQUIRE(kind >= 1 && kind <= 4, "activation kind %d unsupported (1 silu, 2 shifted softplus, 3 sigmoid, 4 tanh)", kind);
   if (n == 0) return 0;
   act_bwd_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, as_stream(stream)>>>(kind, g, x, n, out);
+  GOTEN_CHECK_LAUNCH();
+  return 0;
+}
+
+int goten_mul_add_fwd(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream) {
+  if (n == 0) return 0;
+  mul_add_fwd_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, as_stream(stream)>>>(a, b, c, n, out);
+  GOTEN_CHECK_LAUNCH();
+  return 0;
+}
+
+int goten_mul_add_bwd(const float* g, const float* a, const float* b, int64_t n, float* g_a, float* g_b, void* stream) {
+  if (n == 0) return 0;
+  mul_add_bwd_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, as_stream(stream)>>>(g, a, b, n, g_a, g_b);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

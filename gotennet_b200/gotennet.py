@@ -88,17 +88,22 @@ class GATA(nn.Module):
         if not all(p in _ALLOWED_UPDATE_PARTS for p in parts):
             raise ValueError(f"Invalid edge update parts. Allowed parts are {_ALLOWED_UPDATE_PARTS}")
         # "norm" is accepted and ignored by the reference too (parsed at gotennet.py:149-161, never read again)
-        unsupported = [p for p in parts if p not in ("norej", "gated", "gatedt", "act", "mlp", "mlpa", "norm")]
-        if unsupported:
-            raise NotImplementedError(f"edge_updates parts {unsupported} are outside the accelerated path")
         if aggr != "add":
             raise NotImplementedError("only aggr='add' is implemented in the fused message kernel")
-        if edge_ln and ("mlp" in parts or "mlpa" in parts):
+        two_layer_t = "mlp" in parts or "mlpa" in parts
+        lin_w = 2 if "linwa" in parts else (1 if "linw" in parts else 0)      # reference :178-181 (later `if` wins)
+        lin_ln = 2 if "postln" in parts else (1 if "ln" in parts else 0)      # reference :182-185
+        if edge_ln not in ("", "layer", None) and two_layer_t:
             # reference layers.py:563-566: MLP puts `norm` on every Dense but the last, so edge_ln only exists inside a
             # two-layer gamma_t; with the one-layer gamma_t it changes nothing (no module, no state_dict key)
-            raise NotImplementedError("edge_ln inside a two-layer gamma_t ('mlp' / 'mlpa') is outside the accelerated path")
-        if evec_dim not in (None, n_atom_basis):
-            raise NotImplementedError("evec_dim different from n_atom_basis needs the 'linw' edge update (not implemented)")
+            raise NotImplementedError("edge_ln='batch' / 'instance' inside a two-layer gamma_t is not implemented "
+                                      "(only 'layer')")
+        if evec_dim not in (None, n_atom_basis) and not lin_w and not last_layer and edge_updates:
+            # the reference builds this layer and then fails in edge_update: gamma_t(t) [E,C] * w [E,evec_dim] (:611)
+            raise ValueError("evec_dim different from n_atom_basis needs the 'linw' / 'linwa' edge update (W_edp maps "
+                             "the weight back to n_atom_basis)")
+        if evec_dim is not None and evec_dim % 4 != 0:
+            raise NotImplementedError("evec_dim must be a multiple of 4 (16-byte rows of the projection buffers)")
         if emlp_dim is not None and emlp_dim % 4 != 0:
             raise NotImplementedError("emlp_dim must be a multiple of 4 (16-byte rows of the edge projection buffer)")
         if not is_silu(activation):
@@ -110,7 +115,7 @@ class GATA(nn.Module):
             if name in parts:
                 gated = name
         self.update_info = {"gated": gated, "rej": "norej" not in parts, "mlp": "mlp" in parts, "mlpa": "mlpa" in parts,
-                            "lin_w": 0, "lin_ln": 0}
+                            "lin_w": lin_w, "lin_ln": lin_ln}
         self.sep_htr, self.sep_dir, self.sep_tensor = sep_htr, sep_dir, sep_tensor
         self.epsilon, self.last_layer, self.edge_updates, self.scale_edge = epsilon, last_layer, edge_updates, scale_edge
         self.activation, self.dropout, self.n_atom_basis, self.lmax = activation, dropout, n_atom_basis, lmax
@@ -124,8 +129,11 @@ class GATA(nn.Module):
         self.W_k = mk(C, C, activation=None)
         self.gamma_v = nn.Sequential(mk(C, C, activation=activation), mk(C, multiplier * C, activation=None))
         self.W_re = mk(C, C, activation=activation)
-        self.edge_vec_dim = C
+        self.edge_vec_dim = Ev = C if evec_dim is None else evec_dim
         self.edge_mlp_dim = C if emlp_dim is None else emlp_dim
+        # host-composed refinement (separate launches for the projections, the weight, gamma_w and gamma_t) for the
+        # variants whose gamma_w / gamma_t is a network the HTR kernels do not evaluate in-line
+        self._composed = bool(lin_w) or bool(two_layer_t and edge_ln == "layer")
         if not self.last_layer and self.edge_updates:
             # gamma_t (reference :239-250): one Dense(C -> C, act), or with "mlp" / "mlpa" two layers through emlp_dim,
             # the last one without ("mlp") or with ("mlpa") the activation
@@ -134,14 +142,25 @@ class GATA(nn.Module):
                                last_activation=None if self.update_info["mlp"] else self.activation,
                                norm=edge_ln if two else "",
                                weight_init=weight_init, bias_init=bias_init)
-            self.W_vq = mk(C, C, activation=None, bias=False)
+            self.W_vq = mk(C, Ev, activation=None, bias=False)
             if self.sep_htr:
-                self.W_vk = nn.ModuleList([mk(C, C, activation=None, bias=False) for _ in range(lmax)])
+                self.W_vk = nn.ModuleList([mk(C, Ev, activation=None, bias=False) for _ in range(lmax)])
             else:
-                self.W_vk = mk(C, C, activation=None, bias=False)
-            # gamma_w (reference :270-292): an optional gate on the scalar HTR weight; evaluated inside the HTR kernels
+                self.W_vk = mk(C, Ev, activation=None, bias=False)
+            # gamma_w (reference :270-292): [LayerNorm] -> [activation] -> W_edp (-> LayerNorm) with "linw" / "linwa" /
+            # "ln" / "postln", then an optional gate.  Without "linw" the gate is evaluated inside the HTR kernels.
+            modules = []
+            if lin_w:
+                if lin_ln == 1:
+                    modules.append(nn.LayerNorm(Ev))
+                if lin_w == 2:
+                    # (the reference appends `self.activation` itself and therefore needs an nn.Module here: a string
+                    # activation works, its functional default F.silu raises in nn.Sequential; both are SiLU)
+                    modules.append(activation if isinstance(activation, nn.Module) else nn.SiLU())
+                self.W_edp = mk(Ev, C, activation=None, norm="layer" if lin_ln == 2 else "")
+                modules.append(self.W_edp)
             gate_mod = {"gated": nn.Sigmoid, "gatedt": nn.Tanh, "act": nn.SiLU}.get(gated)
-            self.gamma_w = nn.Sequential(*([gate_mod()] if gate_mod else []))
+            self.gamma_w = nn.Sequential(*(modules + ([gate_mod()] if gate_mod else [])))
         self.cutoff = CosineCutoff(cutoff)
         self._alpha = None
         self.W_rs = mk(C, C * multiplier, activation=None)
@@ -170,6 +189,8 @@ class GATA(nn.Module):
             self.W_vq.reset_parameters()
             for w in (self.W_vk if self.sep_htr else [self.W_vk]):
                 w.reset_parameters()
+            if self.update_info["lin_w"]:
+                self.W_edp.reset_parameters()
         if self.layernorm_:
             self.layernorm.reset_parameters()
         if self.steerable_norm_:
@@ -210,7 +231,8 @@ class GATA(nn.Module):
             Xd = ops.TensorLayerNormFn.apply(Xd, self.tensor_layernorm.weight, self.lmax)
         Wn1 = torch.cat([self.W_q.weight, self.W_k.weight, self.gamma_s[0].weight, self.gamma_v[0].weight], 0)
         bn1 = torch.cat([self.W_q.bias, self.W_k.bias, self.gamma_s[0].bias, self.gamma_v[0].bias], 0)
-        if self.has_htr:
+        fused_htr = self.has_htr and not self._composed
+        if fused_htr:
             gt = self.gamma_t.dense_layers[0]
             We = torch.cat([self.W_re.weight, self.W_rs.weight, gt.weight], 0)
             be = torch.cat([self.W_re.bias, self.W_rs.bias, gt.bias], 0)
@@ -222,14 +244,54 @@ class GATA(nn.Module):
             be = torch.cat([self.W_re.bias, self.W_rs.bias], 0)
             Wvq = Wvk = None
         Wt2 = bt2 = None
-        if self.has_htr and len(self.gamma_t.dense_layers) == 2:
+        if fused_htr and len(self.gamma_t.dense_layers) == 2:
             Wt2, bt2 = self.gamma_t.dense_layers[1].weight, self.gamma_t.dense_layers[1].bias
         out = ops.GataBlockFn.apply(h, Xd, t, Y, fc, kappa, Wn1, bn1, self.gamma_s[1].weight, self.gamma_s[1].bias,
                                     self.gamma_v[1].weight, self.gamma_v[1].bias, We, be, Wvq, Wvk, plan,
                                     self._kernel_cfg(), t_amax, drop, Wt2, bt2)
-        if self.has_htr:
+        if fused_htr:
             return out
+        if self.has_htr:
+            return out[0], out[1], self._refine_composed(plan, out[1], t, Y), out[2]
         return out[0], out[1], t, out[2]
+
+    def _refine_composed(self, plan: GraphPlan, Xd1, t, Y):
+        """t + gamma_t(t) * gamma_w(w) (reference gotennet.py:429-447, :561-611) for the "linw" / "linwa" / "ln" /
+        "postln" edge updates, `evec_dim`, and `edge_ln` inside a two-layer gamma_t: projections, w, gamma_w and gamma_t
+        as separate launches (GEMMs, the weight-only HTR kernels, LayerNorm / activation kernels)."""
+        L, N, C = Xd1.shape
+        Ev, info = self.edge_vec_dim, self.update_info
+        groups = _degree_ranges(self.lmax) if self.sep_htr else [(0, L)]
+        EQ = ops.DenseActFn.apply(Xd1.reshape(L * N, C), self.W_vq.weight, None, ops.ACT_NONE).view(L, N, Ev)
+        vk = list(self.W_vk) if self.sep_htr else [self.W_vk]
+        EK = torch.cat([ops.DenseActFn.apply(Xd1[lo:hi].reshape((hi - lo) * N, C), vk[g].weight, None, ops.ACT_NONE)
+                        for g, (lo, hi) in enumerate(groups)], 0).view(L, N, Ev)
+        flags = (1 if self.sep_htr else 0) | (2 if info["rej"] else 0)
+        u = ops.HtrWeightFn.apply(EQ, EK, Y, plan, self.lmax, flags)                       # w_ij [E, Ev]
+        if info["lin_w"]:
+            if info["lin_ln"] == 1:
+                ln = self.gamma_w[0]
+                u = ops.LayerNormFn.apply(u, ln.weight, ln.bias, ln.eps)
+            if info["lin_w"] == 2:
+                u = ops.ActFn.apply(u, ops.ACT_SILU)
+            u = ops.DenseActFn.apply(u, self.W_edp.weight, self.W_edp.bias, ops.ACT_NONE)
+            if self.W_edp.norm is not None:
+                u = ops.LayerNormFn.apply(u, self.W_edp.norm.weight, self.W_edp.norm.bias, self.W_edp.norm.eps)
+        gate = {False: ops.ACT_NONE, "gated": ops.ACT_SIGMOID, "gatedt": ops.ACT_TANH, "act": ops.ACT_SILU}[info["gated"]]
+        if gate != ops.ACT_NONE:
+            u = ops.ActFn.apply(u, gate)
+        gt = t
+        layers = self.gamma_t.dense_layers
+        for k, d in enumerate(layers):   # Dense = linear -> [LayerNorm] -> [activation] (layers.py:512-529)
+            act = ops.ACT_SILU if d.activation else ops.ACT_NONE
+            if d.norm is not None:
+                gt = ops.DenseActFn.apply(gt, d.weight, d.bias, ops.ACT_NONE)
+                gt = ops.LayerNormFn.apply(gt, d.norm.weight, d.norm.bias, d.norm.eps)
+                if act != ops.ACT_NONE:
+                    gt = ops.ActFn.apply(gt, act)
+            else:
+                gt = ops.DenseActFn.apply(gt, d.weight, d.bias, act)
+        return ops.MulAddFn.apply(gt, u, t)
 
     def forward(self, edge_index: Tensor, h: Tensor, X: Tensor, rl_ij: Tensor, t_ij: Tensor, r_ij: Tensor,
                 n_edges: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
@@ -409,7 +471,8 @@ class GotenNet(nn.Module):
             has_htr = gata.has_htr
             h, Xd, t, hints = gata._block(plan, h, Xd, t, Y, fc, kappa, t_amax,
                                           attn_drop_masks[i] if attn_drop_masks is not None else None)
-            t_amax = hints[1:2] if has_htr else t_amax
+            # (the composed refinement does not report max |t'|: the next block measures it)
+            t_amax = (None if gata._composed else hints[1:2]) if has_htr else t_amax
             h, Xd = eqff._block(h, Xd, hints[0:1])
             if cap is not None:
                 cap[f"h{i + 1}"], cap[f"t{i + 1}"] = h.detach(), t.detach()

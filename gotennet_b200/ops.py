@@ -767,7 +767,7 @@ class EqffBlockFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------
 # read-out head (reference models/components/outputs.py:232-376)
 # ---------------------------------------------------------------------------
-ACT_NONE, ACT_SILU, ACT_SSP = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_SSP, ACT_SIGMOID, ACT_TANH = 0, 1, 2, 3, 4
 
 
 class DenseActFn(torch.autograd.Function):
@@ -801,6 +801,84 @@ class DenseActFn(torch.autograd.Function):
             g = gz
         da, dw, db = linear_bwd(g, x, w, need_da=ctx.needs_input_grad[0], need_bias=ctx.has_bias)
         return da, dw, db, None
+
+
+class ActFn(torch.autograd.Function):
+    """Element-wise activation (goten_act_*): SiLU / shifted softplus / sigmoid / tanh."""
+
+    @staticmethod
+    def forward(ctx, x, kind):
+        _chk(x)
+        x = _f32(x.contiguous())
+        ctx.kind = kind
+        ctx.save_for_backward(x)
+        return _act_apply(kind, x)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.contiguous()
+        out = torch.empty_like(g)
+        lib().call("goten_act_bwd", ctx.kind, _ptr(g), _ptr(x), g.numel(), _ptr(out), _stream())
+        return out, None
+
+
+class MulAddFn(torch.autograd.Function):
+    """a * b + c, all [E, C]: the residual edge update t + gamma_t(t) * gamma_w(w) (gotennet.py:611, :445) of the
+    host-composed HTR variants."""
+
+    @staticmethod
+    def forward(ctx, a, b, c):
+        _chk(a, b, c)
+        a, b, c = a.contiguous(), b.contiguous(), c.contiguous()
+        out = torch.empty_like(a)
+        lib().call("goten_mul_add_fwd", _ptr(a), _ptr(b), _ptr(c), a.numel(), _ptr(out), _stream())
+        ctx.save_for_backward(a, b)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        g_a, g_b = torch.empty_like(a), torch.empty_like(b)
+        lib().call("goten_mul_add_bwd", _ptr(g), _ptr(a), _ptr(b), g.numel(), _ptr(g_a), _ptr(g_b), _stream())
+        return g_a, g_b, g
+
+
+class HtrWeightFn(torch.autograd.Function):
+    """w_ij [E, Ev] = sum over degree groups of rej(EQ_i) . rej(EK_j) (GATA.edge_update up to the gamma_w call,
+    gotennet.py:580-609) from degree-major EQ / EK [L, N, Ev]: the weight-only mode of the HTR kernels (flags bit 5).
+    Gradients: g_EQ, g_EK and, when the geometry needs it (forces), g_Y."""
+
+    @staticmethod
+    def forward(ctx, EQ, EK, Y, plan, lmax, flags):
+        _chk(EQ, EK, Y)
+        EQ, EK, Y = EQ.contiguous(), EK.contiguous(), Y.contiguous()
+        L, N, Ev = EQ.shape
+        w = torch.empty(plan.E, Ev, device=EQ.device)
+        ctx.plan, ctx.lmax, ctx.flags = plan, lmax, flags | 32
+        lib().call("goten_htr_fwd", _ptr(EQ), _ptr(EK), Ev, _ptr(Y), None, 0, 0, None, _ptr(plan.tgt_ptr),
+                   _ptr(plan.src), N, Ev, lmax, ctx.flags, _ptr(w), None, _stream())
+        ctx.save_for_backward(EQ, EK, Y)
+        return w
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_w):
+        EQ, EK, Y = ctx.saved_tensors
+        plan = ctx.plan
+        L, N, Ev = EQ.shape
+        g_w = g_w.contiguous()
+        g_EQ, g_EK = torch.empty_like(EQ), torch.empty_like(EK)
+        g_Y = torch.zeros_like(Y) if ctx.needs_input_grad[2] else None
+        L_, st = lib(), _stream()
+        L_.call("goten_htr_bwd_tgt", _ptr(g_w), _ptr(EQ), _ptr(EK), Ev, _ptr(Y), None, 0, 0, _ptr(plan.tgt_ptr),
+                _ptr(plan.src), N, Ev, ctx.lmax, ctx.flags, _ptr(g_EQ), None, 0, _ptr(g_Y), None, None, st)
+        L_.call("goten_htr_bwd_src", _ptr(g_w), _ptr(EQ), _ptr(EK), Ev, _ptr(Y), None, 0, 0, _ptr(plan.src_ptr),
+                _ptr(plan.src_perm), _ptr(plan.tgt), N, Ev, ctx.lmax, ctx.flags, _ptr(g_EK), None, st)
+        return g_EQ, g_EK, g_Y, None, None, None
 
 
 def mol_ptr_from_batch(batch: torch.Tensor, n_mol: int, check_sorted: bool = True) -> torch.Tensor:

@@ -264,6 +264,8 @@ int goten_gata_bwd_src(const float* g_h, const float* g_Xd, const float* Xd, con
  * weight [W_vq; W_vk]).  flags bits 2-3: gamma_w of the gated edge updates (0 identity,
  * 1 sigmoid "gated", 2 tanh "gatedt", 3 SiLU "act"; gotennet.py:283-289).
  * bit 4: gamma_t ends without activation ("mlp" edge update): zt is used as is.
+ * bit 5: weight only (the "linw" family, gotennet.py:270-282): forward writes t_out[e][c] = w (C = evec_dim; Ze, t
+ * unread, may be NULL); the backward halves take g_t_out = dL/dw and write g_EQ / g_EK (+ g_Y), no gZe.
  * flags: bit0 = sep_htr (rejection per degree),
  * bit1 = rejection enabled.                                                    */
 int goten_htr_fwd(const float* EQ, const float* EK, int ldp, const float* Y, const float* Ze, int ldz,
@@ -318,7 +320,7 @@ int goten_embedding_bwd(const float* g_out, const int64_t* idx, int64_t n, int C
  * as a deterministic segmented reduction over mol_ptr.  mode: 0 none, 1 sum, 2 mean.
  * goten_mol_ptr builds mol_ptr [n_mol+1] from the (sorted) int64 batch vector of a PyG
  * batch; unsorted_flag[0] (device, nullable) is set to 1 when the vector is not sorted.
- * goten_act_*: the head MLP's activations (layers.py:69-81, :619): kind 1 SiLU, 2 shifted
+ * goten_act_*: element-wise activations (layers.py:41-81, :619; 3 sigmoid, 4 tanh): kind 1 SiLU, 2 shifted
  * softplus.                                                                          */
 int goten_mol_ptr(const int64_t* batch, int n_nodes, int n_mol, int32_t* mol_ptr, int32_t* unsorted_flag,
                   void* stream);
@@ -331,6 +333,10 @@ int goten_atomwise_reduce_bwd(const float* g_y, const float* g_yi, const float* 
                               float* g_raw, void* stream);
 int goten_act_fwd(int kind, const float* x, int64_t n, float* y, void* stream);
 int goten_act_bwd(int kind, const float* g, const float* x, int64_t n, float* out, void* stream);
+/* out = a * b + c;  g_a = g * b, g_b = g * a: the residual edge update t + gamma_t(t) * gamma_w(w) (gotennet.py:611,
+ * :445) of the "linw" family, where gamma_w is a network on w (LayerNorm / activation / goten_gemm launches).       */
+int goten_mul_add_fwd(const float* a, const float* b, const float* c, int64_t n, float* out, void* stream);
+int goten_mul_add_bwd(const float* g, const float* a, const float* b, int64_t n, float* g_a, float* g_b, void* stream);
 
 /* ------------------------------- equivariant read-out heads --
  * Element-wise / per-molecule stages of GatedEquivariantBlock (models/components/outputs.py:24-104: vmix [N][3][2*nv]

@@ -68,6 +68,23 @@ NORM_CASES["eu_mlp"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, 
 NORM_CASES["eu_mlpa_gated"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=3, lmax=1, num_heads=4,
                                                     edge_updates="mlpa_gated"), atoms=[13, 4], seed=17)
 
+# gamma_w as a network on the HTR weight ("linw" / "linwa" with "ln" / "postln", evec_dim) and LayerNorm inside a
+# two-layer gamma_t (edge_ln) - reference gotennet.py:178-185, :236, :249, :270-282.  "linwa" needs a Module
+# activation in the reference (a string one; its functional default fails in nn.Sequential): `activation` below is
+# what the generator passes to the reference constructor.
+NORM_CASES["eu_linw_ln_ev"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=3, lmax=2, num_heads=4, sep_dir=True,
+                                                    sep_tensor=True, scale_edge=False, edge_updates="linw_ln",
+                                                    evec_dim=24), atoms=[12, 7], seed=18)
+NORM_CASES["eu_linwa_postln_gated"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=1, num_heads=4,
+                                                            edge_updates="linwa_postln_gated_norej", evec_dim=48),
+                                           atoms=[9, 11], seed=19, activation="silu")
+NORM_CASES["eu_linw_nosep"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, num_heads=4,
+                                                    sep_htr=False, edge_updates="linw_mlp", emlp_dim=40),
+                                   atoms=[13, 5], seed=20)
+NORM_CASES["eu_mlpa_edgeln"] = dict(cfg=OracleConfig(n_atom_basis=32, n_interactions=2, lmax=2, num_heads=4, sep_dir=True,
+                                                     sep_tensor=True, scale_edge=False, edge_updates="mlpa_gatedt",
+                                                     emlp_dim=48, edge_ln="layer"), atoms=[10, 8], seed=22)
+
 # read-out head cases: representation + Atomwise energy head with forces.  `rep` names the
 # representation config; head = Atomwise(n_in=C, activation=..., mean, stddev, atomref, derivative="forces")
 HEAD_CASES = {

@@ -55,6 +55,8 @@ class OracleConfig:
     sep_tensor: bool = False
     max_num_neighbors: int = 32
     emlp_dim: Optional[int] = None  # width of gamma_t's hidden layer with the "mlp" / "mlpa" edge updates (:236-242)
+    evec_dim: Optional[int] = None  # width of the W_vq / W_vk projections (:236, :252-268); != C needs "linw" / "linwa"
+    edge_ln: str = ""               # "layer": LayerNorm inside a two-layer gamma_t (MLP norm, :249, layers.py:563-566)
     radial_basis: str = "expnorm"   # "expnorm" | "BesselBasis" | "GaussianRBF" (layers.py:749-777)
     layernorm: str = ""        # != "": nn.LayerNorm on h at the top of every GATA block (gotennet.py:308-310, :397)
     steerable_norm: str = ""   # != "": TensorLayerNorm on X (gotennet.py:311-315, :398)
@@ -131,12 +133,26 @@ def state_dict_spec(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]
             else:
                 sp.append((p + "gamma_t.dense_layers.0.weight", (C, C), "weight"))
                 sp.append((p + "gamma_t.dense_layers.0.bias", (C,), "bias"))
-            sp.append((p + "W_vq.weight", (C, C), "weight"))
+            if cfg.edge_ln and ("mlp" in eu or "mlpa" in eu):          # Dense(norm="layer") on the hidden layer
+                sp.append((p + "gamma_t.dense_layers.0.norm.weight", (cfg.emlp_dim or C,), "ln_w"))
+                sp.append((p + "gamma_t.dense_layers.0.norm.bias", (cfg.emlp_dim or C,), "ln_b"))
+            Ev = cfg.evec_dim or C
+            sp.append((p + "W_vq.weight", (Ev, C), "weight"))
             if cfg.sep_htr:
                 for l in range(cfg.lmax):
-                    sp.append((p + f"W_vk.{l}.weight", (C, C), "weight"))
+                    sp.append((p + f"W_vk.{l}.weight", (Ev, C), "weight"))
             else:
-                sp.append((p + "W_vk.weight", (C, C), "weight"))
+                sp.append((p + "W_vk.weight", (Ev, C), "weight"))
+            lin_w, lin_ln = edge_lin_flags(cfg)
+            if lin_w:                                                  # gamma_w network, gotennet.py:270-282
+                if lin_ln == 1:
+                    sp.append((p + "gamma_w.0.weight", (Ev,), "ln_w"))
+                    sp.append((p + "gamma_w.0.bias", (Ev,), "ln_b"))
+                sp.append((p + "W_edp.weight", (C, Ev), "weight"))
+                sp.append((p + "W_edp.bias", (C,), "bias"))
+                if lin_ln == 2:
+                    sp.append((p + "W_edp.norm.weight", (C,), "ln_w"))
+                    sp.append((p + "W_edp.norm.bias", (C,), "ln_b"))
     for i in range(cfg.n_interactions):
         p = f"eqff_list.{i}."
         sp.append((p + "gamma_m.0.weight", (C, 2 * C), "weight"))
@@ -145,6 +161,15 @@ def state_dict_spec(cfg: OracleConfig) -> List[Tuple[str, Tuple[int, ...], str]]
         sp.append((p + "gamma_m.1.bias", (2 * C,), "bias"))
         sp.append((p + "W_vu.weight", (C, C), "weight"))
     return sp
+
+
+def edge_lin_flags(cfg: OracleConfig) -> Tuple[int, int]:
+    """(lin_w, lin_ln) of GATA.update_info (gotennet.py:178-185): lin_w 1 = "linw", 2 = "linwa" (activation before
+    W_edp); lin_ln 1 = "ln" (LayerNorm on w before W_edp), 2 = "postln" (LayerNorm after W_edp)."""
+    parts = cfg.edge_updates.split("_") if isinstance(cfg.edge_updates, str) else []
+    lin_w = 2 if "linwa" in parts else (1 if "linw" in parts else 0)
+    lin_ln = 2 if "postln" in parts else (1 if "ln" in parts else 0)
+    return lin_w, lin_ln
 
 
 def rbf_buffers(cfg: OracleConfig, dtype=torch.float32) -> Tuple[Tensor, Tensor]:
@@ -194,13 +219,21 @@ def make_state_dict(cfg: OracleConfig, seed: int = 0, bias_scale: float = 0.1,
     return sd
 
 
-def expand_aliases(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+def expand_aliases(sd: Dict[str, Tensor], cfg: Optional[OracleConfig] = None) -> Dict[str, Tensor]:
     """MLP registers each Dense under `dense_layers.i` AND `layers.i`
-    (layers.py:566-571): add the aliased duplicate keys the reference expects."""
+    (layers.py:566-571): add the aliased duplicate keys the reference expects.  With the "linw" edge updates `W_edp`
+    is both an attribute and an element of the `gamma_w` Sequential (gotennet.py:277-292): its position there depends
+    on the switches, hence `cfg`."""
     out = dict(sd)
     for k, v in sd.items():
         if ".dense_layers." in k:
             out[k.replace(".dense_layers.", ".layers.")] = v
+        if ".W_edp." in k:
+            if cfg is None:
+                raise ValueError("expand_aliases needs cfg for the gamma_w aliases of W_edp")
+            lin_w, lin_ln = edge_lin_flags(cfg)
+            pos = (1 if lin_ln == 1 else 0) + (1 if lin_w == 2 else 0)
+            out[k.replace(".W_edp.", f".gamma_w.{pos}.")] = v
     return out
 
 
@@ -419,13 +452,26 @@ def gata_layer(sd, cfg: OracleConfig, i: int, edge_index, h, X, Y, t, r, n_edges
                 Kr = Kr - (Kr * y).sum(1, keepdim=True) * y
             w = w + (Qr * Kr).sum(1)
         parts = cfg.edge_updates.split("_") if isinstance(cfg.edge_updates, str) else []
+        lin_w, lin_ln = edge_lin_flags(cfg)
+        if lin_w:                                                      # gamma_w network on w [E, evec_dim], :270-282
+            if lin_ln == 1:
+                w = F.layer_norm(w, w.shape[-1:], sd[p + "gamma_w.0.weight"], sd[p + "gamma_w.0.bias"], 1e-5)
+            if lin_w == 2:
+                w = F.silu(w)
+            w = _lin(sd, p + "W_edp", w)
+            if lin_ln == 2:                                            # Dense(norm="layer"): after the linear map
+                w = F.layer_norm(w, w.shape[-1:], sd[p + "W_edp.norm.weight"], sd[p + "W_edp.norm.bias"], 1e-5)
         if "act" in parts:                                             # gamma_w, :283-289 (later parts win, :168-173)
             w = F.silu(w)
         elif "gatedt" in parts:
             w = torch.tanh(w)
         elif "gated" in parts:
             w = torch.sigmoid(w)
-        gt = F.silu(_lin(sd, p + "gamma_t.dense_layers.0", t))
+        gt = _lin(sd, p + "gamma_t.dense_layers.0", t)
+        if cfg.edge_ln and ("mlp" in parts or "mlpa" in parts):        # Dense: linear -> norm -> activation (layers.py:523-528)
+            gt = F.layer_norm(gt, gt.shape[-1:], sd[p + "gamma_t.dense_layers.0.norm.weight"],
+                              sd[p + "gamma_t.dense_layers.0.norm.bias"], 1e-5)
+        gt = F.silu(gt)
         if "mlp" in parts or "mlpa" in parts:                          # MLP([C, emlp, C]), last activation None for "mlp"
             gt = _lin(sd, p + "gamma_t.dense_layers.1", gt)
             if "mlp" not in parts:

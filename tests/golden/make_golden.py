@@ -33,10 +33,11 @@ from oracle.ref_standins import import_reference  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def build_reference(ref, cfg: orc.OracleConfig):
+def build_reference(ref, cfg: orc.OracleConfig, **extra):
     from gotennet.models.components.layers import CosineCutoff
 
     return ref.GotenNetWrapper(
+        evec_dim=cfg.evec_dim, edge_ln=cfg.edge_ln, **extra,
         n_atom_basis=cfg.n_atom_basis, n_interactions=cfg.n_interactions, n_rbf=cfg.n_rbf,
         cutoff_fn=CosineCutoff(cfg.cutoff), max_z=cfg.max_z, epsilon=cfg.epsilon, num_heads=cfg.num_heads,
         attn_dropout=0.0, edge_updates=cfg.edge_updates, scale_edge=cfg.scale_edge, lmax=cfg.lmax,
@@ -51,8 +52,8 @@ def run_case(ref, name, spec, save=True):
     cfg = spec["cfg"]
     z, pos, batch = _blob(spec["atoms"], spec["seed"])
     sd = orc.make_state_dict(cfg, seed=spec["seed"])
-    model = build_reference(ref, cfg)
-    missing = model.load_state_dict(orc.expand_aliases(sd), strict=True)
+    model = build_reference(ref, cfg, **({"activation": spec["activation"]} if "activation" in spec else {}))
+    missing = model.load_state_dict(orc.expand_aliases(sd, cfg), strict=True)
     assert not missing.missing_keys and not missing.unexpected_keys
     model.eval()
 
@@ -99,6 +100,8 @@ def run_case(ref, name, spec, save=True):
     seen = set()
     for k, p in model.named_parameters():  # named_parameters de-duplicates aliases
         key = k.replace(".layers.", ".dense_layers.") if ("W_ndp" in k or "W_nrd_nru" in k or "gamma_t" in k) else k
+        if ".gamma_w." in key and key not in sd:   # W_edp seen through the gamma_w Sequential first: canonical name
+            key = key[:key.index(".gamma_w.")] + ".W_edp." + key.split(".gamma_w.")[1].split(".", 1)[1]
         if key in seen:
             continue
         seen.add(key)

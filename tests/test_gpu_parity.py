@@ -47,8 +47,9 @@ def build(g, cfg, sd, dev, **kw):
                           num_heads=cfg.num_heads, edge_updates=cfg.edge_updates, scale_edge=cfg.scale_edge,
                           lmax=cfg.lmax, sep_htr=cfg.sep_htr, sep_dir=cfg.sep_dir, sep_tensor=cfg.sep_tensor,
                           max_num_neighbors=cfg.max_num_neighbors, activation="swish", layernorm=cfg.layernorm,
-                          steerable_norm=cfg.steerable_norm, radial_basis=cfg.radial_basis, emlp_dim=cfg.emlp_dim, **kw)
-    m.load_state_dict(orc.expand_aliases(sd), strict=True)
+                          steerable_norm=cfg.steerable_norm, radial_basis=cfg.radial_basis, emlp_dim=cfg.emlp_dim,
+                          evec_dim=cfg.evec_dim, edge_ln=cfg.edge_ln, **kw)
+    m.load_state_dict(orc.expand_aliases(sd, cfg), strict=True)
     return m.to(dev)
 
 

@@ -55,7 +55,13 @@ def test_state_dict_matches_reference_module(g):
     for kw in (dict(n_atom_basis=64, n_interactions=2, lmax=1),
                dict(n_atom_basis=32, n_interactions=3, lmax=3, sep_dir=True, sep_tensor=True, sep_htr=False),
                # switches that are no-ops in the reference (no module, no key): "norm", edge_ln with a one-layer gamma_t
-               dict(n_atom_basis=32, n_interactions=2, lmax=2, edge_updates="norm_gated", edge_ln="layer")):
+               dict(n_atom_basis=32, n_interactions=2, lmax=2, edge_updates="norm_gated", edge_ln="layer"),
+               # gamma_w networks (W_edp aliased into the gamma_w Sequential), evec_dim, edge_ln inside a two-layer gamma_t
+               dict(n_atom_basis=32, n_interactions=2, lmax=2, edge_updates="linw_ln", evec_dim=24),
+               dict(n_atom_basis=32, n_interactions=2, lmax=1, edge_updates="linwa_postln_gated", activation="silu"),
+               dict(n_atom_basis=32, n_interactions=3, lmax=2, edge_updates="linw_ln_postln_act_mlp", emlp_dim=40,
+                    sep_htr=False, evec_dim=16),
+               dict(n_atom_basis=32, n_interactions=2, lmax=2, edge_updates="mlpa", emlp_dim=48, edge_ln="layer")):
         a = ref.GotenNetWrapper(cutoff_fn=CosineCutoff(5.0), **kw).state_dict()
         b = g.GotenNetWrapper(cutoff_fn=g.CosineCutoff(5.0), **kw).state_dict()
         assert set(a) == set(b)
@@ -77,8 +83,13 @@ def test_constructor_errors(g):
         g.GotenNet()  # cutoff_fn is mandatory (the reference dies with AttributeError, gotennet.py:839)
     with pytest.raises(ValueError):
         g.GATA(64, torch.nn.functional.silu, edge_updates="bogus")  # gotennet.py:164-167
+    with pytest.raises(ValueError):   # gamma_t(t) [E,C] * w [E,evec_dim] cannot broadcast without W_edp (gotennet.py:611)
+        g.GATA(64, torch.nn.functional.silu, evec_dim=32)
     with pytest.raises(NotImplementedError):
-        g.GATA(64, torch.nn.functional.silu, edge_updates="linw")
+        g.GATA(64, torch.nn.functional.silu, edge_updates="mlp", edge_ln="batch")
+    lw = g.GATA(64, torch.nn.functional.silu, edge_updates="linwa_ln_gatedt", evec_dim=32)
+    assert [type(x).__name__ for x in lw.gamma_w] == ["LayerNorm", "SiLU", "Dense", "Tanh"] and lw.gamma_w[2] is lw.W_edp
+    assert lw.W_vq.weight.shape == (32, 64) and lw.W_edp.weight.shape == (64, 32) and lw._composed
     assert isinstance(g.GATA(64, torch.nn.functional.silu, edge_updates="gated_gatedt").gamma_w[0], torch.nn.Tanh)
     m = g.GotenNet(n_atom_basis=32, n_interactions=1, cutoff_fn=g.CosineCutoff(5.0), radial_basis="BesselBasis", n_rbf=8)
     assert set(k for k in m.state_dict() if k.startswith("radial_basis.")) == {"radial_basis.freqs", "radial_basis.norm1"}

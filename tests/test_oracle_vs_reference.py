@@ -32,7 +32,7 @@ def _same(out, path):
         assert np.array_equal(np.asarray(out[k]), gold[k]), k
 
 
-@pytest.mark.parametrize("name", ["cfg1", "yaml_l2", "l3_trunc", "eu_mlp"])
+@pytest.mark.parametrize("name", ["cfg1", "yaml_l2", "l3_trunc", "eu_mlp", "eu_linw_ln_ev", "eu_linwa_postln_gated"])
 def test_representation_fixture_regenerates_bit_identically(ref, name, golden_dir):
     import make_golden
     from oracle.golden_cases import CASES, NORM_CASES
