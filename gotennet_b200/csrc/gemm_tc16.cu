@@ -44,6 +44,7 @@ struct Params {
   int add_vec, c_vec, act_vec;
   int red_add;            // add_src == C: accumulate into C with a TMA reduction store
   int act_tma;            // SiLU side output through a second TMA store (tmAct)
+  int dbg;                // GOTEN_GEMM_DBG (timing experiments only, results are wrong: 4 skip the operand split, 8 skip the output stores)
   float* partial;
   float* colsum;
   float* partial_colsum;
@@ -199,7 +200,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint8_t* a_raw = smem + s * STAGE_BYTES;
         uint8_t* hi_row = a_raw + ct * 128;
         uint8_t* lo_row = hi_row + A_BYTES / 2;
-        if (!A_ROWS_ARE_K) {
+        if (!A_ROWS_ARE_K && (p.dbg & 4)) {
+        } else if (!A_ROWS_ARE_K) {
           // thread = tile row: its 64 floats live in row ct of the two raw boxes and are replaced by row ct of the
           // hi tile (first box) and of the lo tile (second box).  All loads are issued before the first store.
           float4 v[16];
@@ -665,6 +667,7 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
   p.red_add = red_add ? 1 : 0;
   p.act_tma = act_tma ? 1 : 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GOTEN_GEMM_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
   p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
   p.act_vec = (act_out != nullptr && aligned16(act_out) && ld_act % 4 == 0 && act_lo % 4 == 0) ? 1 : 0;

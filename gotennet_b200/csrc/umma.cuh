@@ -203,6 +203,137 @@ __device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, 128;
 //   fused path: read the block back row-wise and do coalesced global stores with the residual add and the SiLU side
 //               output (8 lanes x float4 = one 128 B row segment, 4 rows per instruction).
 // P needs: M, N, C, ldc, bias, add_src, ld_add, act_out, ld_act, act_lo, act_hi, add_vec, c_vec, act_vec, partial, red_add, act_tma.
+// explicit shared-space vector accesses of the staging blocks (a generic pointer makes the compiler emit ST.E / LD.E)
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+// 32 consecutive fp32 accumulator columns of this thread's TMEM lane; completes at the next tcgen05.wait::ld
+#define GOTEN_LDTM_X32(r, taddr)                                                                                      \
+  asm volatile(                                                                                                       \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                       \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                       \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),    \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),        \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                     \
+      : "r"(taddr))
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// One 32x32 block of the epilogue: registers (thread = row, 32 columns) -> un-scale + bias -> swizzled smem block ->
+// TMA store(s) (fast) or the row-wise register path with residual / SiLU side output.  `blv`: the tile's bias, lane l
+// holding columns n0 + 8 l .. 8 l + 7; column c of chunk ch sits in lane 4 ch + c / 8, slot c % 8.
+template <class P>
+__device__ __forceinline__ void epilogue_block(const P& p, const CUtensorMap& tmC, const CUtensorMap& tmAct, const uint32_t (&r)[32],
+                                               const float (&blv)[8], int ch, int nc0, int row_base, int split,
+                                               uint32_t my_buf, uint32_t& n_store, int lane, float un, bool fast) {
+  if (p.dbg & 8) return;
+  const uint32_t buf = my_buf + (n_store & 1) * 4096;
+  if (fast && n_store >= 2) {
+    if (lane == 0) bulk_wait_read<1>();
+    __syncwarp();
+  }
+  const int l0 = ch * 4;
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    float4 v;
+    v.x = fmaf(__uint_as_float(r[4 * c + 0]), un, __shfl_sync(0xffffffffu, blv[(4 * c + 0) & 7], l0 + (c >> 1)));
+    v.y = fmaf(__uint_as_float(r[4 * c + 1]), un, __shfl_sync(0xffffffffu, blv[(4 * c + 1) & 7], l0 + (c >> 1)));
+    v.z = fmaf(__uint_as_float(r[4 * c + 2]), un, __shfl_sync(0xffffffffu, blv[(4 * c + 2) & 7], l0 + (c >> 1)));
+    v.w = fmaf(__uint_as_float(r[4 * c + 3]), un, __shfl_sync(0xffffffffu, blv[(4 * c + 3) & 7], l0 + (c >> 1)));
+    sts128(buf + lane * 128 + ((c ^ (lane & 7)) << 4), v);
+  }
+  if (fast) {
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      if (p.partial) tma_store_2d(&tmC, buf, nc0, split * p.M + row_base);
+      else if (p.red_add) tma_reduce_add_2d(&tmC, buf, nc0, row_base);
+      else tma_store_2d(&tmC, buf, nc0, row_base);
+      bulk_commit();
+    }
+    ++n_store;
+    if (p.act_tma && nc0 >= p.act_lo && nc0 < p.act_hi) {   // warp-uniform: SiLU side output of this block
+      const uint32_t buf2 = my_buf + (n_store & 1) * 4096;
+      if (n_store >= 2) {
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 v = lds128(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
+        v.x = __fdividef(v.x, 1.0f + __expf(-v.x)); v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
+        v.z = __fdividef(v.z, 1.0f + __expf(-v.z)); v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+        sts128(buf2 + lane * 128 + ((c ^ (lane & 7)) << 4), v);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmAct, buf2, nc0 - p.act_lo, row_base);
+        bulk_commit();
+      }
+      ++n_store;
+    }
+    return;
+  }
+  __syncwarp();
+  const int cq = lane & 7, rsub = lane >> 3;
+  const int n = nc0 + cq * 4;
+  const bool vec_ok = (n + 3 < p.N);
+  float4 addv[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub, m = row_base + rr;
+    addv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.add_src && m < p.M) {
+      const float* ap = p.add_src + (size_t)m * p.ld_add + n;
+      if (vec_ok && p.add_vec) addv[i] = *reinterpret_cast<const float4*>(ap);
+      else {
+        if (n + 0 < p.N) addv[i].x = ap[0];
+        if (n + 1 < p.N) addv[i].y = ap[1];
+        if (n + 2 < p.N) addv[i].z = ap[2];
+        if (n + 3 < p.N) addv[i].w = ap[3];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int rr = i * 4 + rsub, m = row_base + rr;
+    float4 v = lds128(buf + rr * 128 + ((cq ^ (rr & 7)) << 4));
+    v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
+    if (m < p.M) {
+      float* cp = p.C + (size_t)m * p.ldc + n;
+      if (vec_ok && p.c_vec) *reinterpret_cast<float4*>(cp) = v;
+      else {
+        if (n + 0 < p.N) cp[0] = v.x;
+        if (n + 1 < p.N) cp[1] = v.y;
+        if (n + 2 < p.N) cp[2] = v.z;
+        if (n + 3 < p.N) cp[3] = v.w;
+      }
+      if (p.act_out && p.act_vec && n >= p.act_lo && n + 3 < p.act_hi) {  // whole float4 inside the SiLU range
+        float4 a;
+        a.x = __fdividef(v.x, 1.0f + __expf(-v.x)); a.y = __fdividef(v.y, 1.0f + __expf(-v.y));
+        a.z = __fdividef(v.z, 1.0f + __expf(-v.z)); a.w = __fdividef(v.w, 1.0f + __expf(-v.w));
+        *reinterpret_cast<float4*>(p.act_out + (size_t)m * p.ld_act + (n - p.act_lo)) = a;
+      } else if (p.act_out) {
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+          const int nn = n + qd;
+          if (nn < p.N && nn >= p.act_lo && nn < p.act_hi)
+            p.act_out[(size_t)m * p.ld_act + (nn - p.act_lo)] = vv[qd] / (1.0f + __expf(-vv[qd]));
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
+
 template <int NCTA, int BM, int EPI_WARP0, class P>
 __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC, const CUtensorMap& tmAct, uint8_t* epi_smem,
                                               uint32_t bar_tfull,
@@ -210,145 +341,70 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
                                               int n_units, int n_items, int n_tiles, int BN, uint32_t rank, float un_a,
                                               float un_b) {
   // =============================== epilogue ===================================
+  // The four warps were the slowest stage of the short-K GEMMs (ncu source view, round 2: busy 87 % of the time, one
+  // warp per scheduler running a serial chain tcgen05.ld -> bias LDG -> generic ST -> fence -> TMA per 32-column
+  // chunk).  Now: the tile's bias is fetched before the accumulator wait, the TMEM load of chunk ch + 1 is in flight
+  // while chunk ch is processed (two register buffers), the accumulator stage is handed back to the MMA warp as soon
+  // as the last load has landed, and the staging block is written with st.shared.
   const int q = warp & 3;
-  uint8_t* my_buf = epi_smem + (warp - EPI_WARP0) * 2 * 4096;
+  const uint32_t my_buf = smem_u32(epi_smem) + (uint32_t)(warp - EPI_WARP0) * 2 * 4096;
   // red_add: the residual already sits in C (add_src == C): the tile is ADDED to it by a TMA reduction store, so the
-  // residual never passes through the SM (the register path below moves 4 KB per warp and round trip)
+  // residual never passes through the SM (the register path moves 4 KB per warp and round trip)
   // act_tma: the SiLU side output (columns [act_lo, act_hi), act_lo a multiple of 32) leaves through a second TMA store of
   // the same 32x32 block (tmAct is a map over act_out with act_hi - act_lo columns, so the range end clips for free)
   const bool fast = (p.add_src == nullptr || p.red_add) && (p.act_out == nullptr || p.act_tma);
+  const float un = un_a * un_b;
   uint32_t tile_it = 0, n_store = 0;
   for (int w = unit; w < n_items; w += n_units, ++tile_it) {
     const int split = w / n_tiles, tile = w % n_tiles;
     const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN;
     const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
-    mbar_wait(bar_tfull + 8 * acc, aph);
-    tc_fence_after();
     const int row_base = m0 + q * 32;
     const bool rows_live = row_base < p.M;
-    for (int ch = 0; ch < BN / 32; ++ch) {
-      const int nc0 = n0 + ch * 32;
-      if (nc0 >= p.N) break;
-      const uint32_t taddr = tmem_base + acc * (uint32_t)BN + ch * 32 + ((uint32_t)(q * 32) << 16);
-      uint32_t r[32];
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-            "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-            "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (!rows_live) continue;
-      float bl = 0.f;
-      if (p.bias && !p.partial && nc0 + lane < p.N) bl = p.bias[nc0 + lane];
-      uint8_t* buf = my_buf + (n_store & 1) * 4096;
-      if (fast && n_store >= 2) {
-        if (lane == 0) bulk_wait_read<1>();
-        __syncwarp();
-      }
+    const int nch = rows_live ? min(BN, p.N - n0 + 31) / 32 : 0;   // 32-column chunks with a live column
+    float blv[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 v;
-        v.x = __uint_as_float(r[4 * c + 0]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 0);
-        v.y = __uint_as_float(r[4 * c + 1]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 1);
-        v.z = __uint_as_float(r[4 * c + 2]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 2);
-        v.w = __uint_as_float(r[4 * c + 3]) * un_a * un_b + __shfl_sync(0xffffffffu, bl, 4 * c + 3);
-        *reinterpret_cast<float4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
-      }
-      if (fast) {
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          if (p.partial) tma_store_2d(&tmC, smem_u32(buf), nc0, split * p.M + row_base);
-          else if (p.red_add) tma_reduce_add_2d(&tmC, smem_u32(buf), nc0, row_base);
-          else tma_store_2d(&tmC, smem_u32(buf), nc0, row_base);
-          bulk_commit();
-        }
-        ++n_store;
-        if (p.act_tma && nc0 >= p.act_lo && nc0 < p.act_hi) {   // warp-uniform: SiLU side output of this block
-          uint8_t* buf2 = my_buf + (n_store & 1) * 4096;
-          if (n_store >= 2) {
-            if (lane == 0) bulk_wait_read<1>();
-            __syncwarp();
-          }
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 v = *reinterpret_cast<const float4*>(buf + lane * 128 + ((c ^ (lane & 7)) << 4));
-            v.x = __fdividef(v.x, 1.0f + __expf(-v.x)); v.y = __fdividef(v.y, 1.0f + __expf(-v.y));
-            v.z = __fdividef(v.z, 1.0f + __expf(-v.z)); v.w = __fdividef(v.w, 1.0f + __expf(-v.w));
-            *reinterpret_cast<float4*>(buf2 + lane * 128 + ((c ^ (lane & 7)) << 4)) = v;
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmAct, smem_u32(buf2), nc0 - p.act_lo, row_base);
-            bulk_commit();
-          }
-          ++n_store;
-        }
+    for (int k = 0; k < 8; ++k) blv[k] = 0.f;
+    if (p.bias && !p.partial && nch > 0) {
+      const int nb = n0 + lane * 8;
+      if (nb + 7 < p.N && (reinterpret_cast<uintptr_t>(p.bias + nb) & 15) == 0) {
+        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + nb), b1 = *reinterpret_cast<const float4*>(p.bias + nb + 4);
+        blv[0] = b0.x; blv[1] = b0.y; blv[2] = b0.z; blv[3] = b0.w;
+        blv[4] = b1.x; blv[5] = b1.y; blv[6] = b1.z; blv[7] = b1.w;
       } else {
-        __syncwarp();
-        const int cq = lane & 7, rsub = lane >> 3;
-        const int n = nc0 + cq * 4;
-        const bool vec_ok = (n + 3 < p.N);
-        float4 addv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rsub, m = row_base + rr;
-          addv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.add_src && m < p.M) {
-            const float* ap = p.add_src + (size_t)m * p.ld_add + n;
-            if (vec_ok && p.add_vec) addv[i] = *reinterpret_cast<const float4*>(ap);
-            else {
-              if (n + 0 < p.N) addv[i].x = ap[0];
-              if (n + 1 < p.N) addv[i].y = ap[1];
-              if (n + 2 < p.N) addv[i].z = ap[2];
-              if (n + 3 < p.N) addv[i].w = ap[3];
-            }
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rsub, m = row_base + rr;
-          float4 v = *reinterpret_cast<const float4*>(buf + rr * 128 + ((cq ^ (rr & 7)) << 4));
-          v.x += addv[i].x; v.y += addv[i].y; v.z += addv[i].z; v.w += addv[i].w;
-          if (m < p.M) {
-            float* cp = p.C + (size_t)m * p.ldc + n;
-            if (vec_ok && p.c_vec) *reinterpret_cast<float4*>(cp) = v;
-            else {
-              if (n + 0 < p.N) cp[0] = v.x;
-              if (n + 1 < p.N) cp[1] = v.y;
-              if (n + 2 < p.N) cp[2] = v.z;
-              if (n + 3 < p.N) cp[3] = v.w;
-            }
-            if (p.act_out && p.act_vec && n >= p.act_lo && n + 3 < p.act_hi) {  // whole float4 inside the SiLU range
-              float4 a;
-              a.x = __fdividef(v.x, 1.0f + __expf(-v.x)); a.y = __fdividef(v.y, 1.0f + __expf(-v.y));
-              a.z = __fdividef(v.z, 1.0f + __expf(-v.z)); a.w = __fdividef(v.w, 1.0f + __expf(-v.w));
-              *reinterpret_cast<float4*>(p.act_out + (size_t)m * p.ld_act + (n - p.act_lo)) = a;
-            } else if (p.act_out) {
-              const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-              for (int qd = 0; qd < 4; ++qd) {
-                const int nn = n + qd;
-                if (nn < p.N && nn >= p.act_lo && nn < p.act_hi)
-                  p.act_out[(size_t)m * p.ld_act + (nn - p.act_lo)] = vv[qd] / (1.0f + __expf(-vv[qd]));
-              }
-            }
-          }
-        }
-        __syncwarp();
+        for (int k = 0; k < 8; ++k)
+          if (nb + k < p.N) blv[k] = p.bias[nb + k];
       }
     }
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) {
-      if (NCTA == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
-      else mbar_arrive(bar_tempty + 8 * acc);
+    mbar_wait(bar_tfull + 8 * acc, aph);
+    tc_fence_after();
+    const uint32_t tbase = tmem_base + acc * (uint32_t)BN + ((uint32_t)(q * 32) << 16);
+    uint32_t rA[32], rB[32];
+    bool released = false;
+    auto release = [&]() {   // every tcgen05.ld of this tile has completed: the MMA warp may overwrite the stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (NCTA == 2) mbar_arrive_cluster(bar_tempty + 8 * acc, 0);
+        else mbar_arrive(bar_tempty + 8 * acc);
+      }
+      released = true;
+    };
+    if (nch > 0) GOTEN_LDTM_X32(rA, tbase);
+    for (int ch = 0; ch < nch; ch += 2) {
+      tmem_wait_ld();
+      if (ch + 1 < nch) GOTEN_LDTM_X32(rB, tbase + (ch + 1) * 32);
+      else release();
+      epilogue_block(p, tmC, tmAct, rA, blv, ch, n0 + ch * 32, row_base, split, my_buf, n_store, lane, un, fast);
+      if (ch + 1 < nch) {
+        tmem_wait_ld();
+        if (ch + 2 < nch) GOTEN_LDTM_X32(rA, tbase + (ch + 2) * 32);
+        else release();
+        epilogue_block(p, tmC, tmAct, rB, blv, ch + 1, n0 + (ch + 1) * 32, row_base, split, my_buf, n_store, lane, un, fast);
+      }
     }
+    if (!released) release();
   }
   if (fast && lane == 0) bulk_wait_all();
 }
