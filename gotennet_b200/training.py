@@ -110,24 +110,24 @@ def force_matching_backward(model, head, batch, loss_fn: Callable[[torch.Tensor,
 
     total = [torch.zeros_like(p) for p in params]
     if gE is not None:   # energy part: exact, on the graph of the first pass
-        for t, g in zip(total, grads_of(lambda: E.backward(gradient=gE))):
-            t.add_(g)
+        torch._foreach_add_(total, grads_of(lambda: E.backward(gradient=gE)))
     scale = float(u.abs().max()) if u is not None else 0.0
     if scale > 0.0:      # force part: -d/deps grad_theta E_total(pos + eps u) at eps = 0
         uhat = (u / scale).detach()
         base = batch.pos.detach()
+        # central-difference weights of d/deps for the stencil pairs (+s h, -s h): each pair is differenced first (the
+        # subtraction of two nearly equal gradients is exact) and folded into `total` with one multi-tensor axpy, so at
+        # most two gradient sets are alive at a time
+        weights = {1.0: 1.0 / (2.0 * h)} if order == 2 else {1.0: 8.0 / (12.0 * h), 2.0: -1.0 / (12.0 * h)}
 
-        def G(s):
-            return grads_of(lambda: _energy(model, head, batch, base + s * h * uhat, plan, masks).sum().backward())
+        def G(s_):
+            return grads_of(lambda: _energy(model, head, batch, base + s_ * h * uhat, plan, masks).sum().backward())
 
-        gp, gm = G(1.0), G(-1.0)
-        if order == 2:
-            fd = [(a - b) / (2.0 * h) for a, b in zip(gp, gm)]
-        else:
-            gp2, gm2 = G(2.0), G(-2.0)
-            fd = [(8.0 * (a - b) - (c - d)) / (12.0 * h) for a, b, c, d in zip(gp, gm, gp2, gm2)]
-        for t, g in zip(total, fd):
-            t.add_(g, alpha=-scale)
+        for s_, w_ in weights.items():
+            gp, gm = G(s_), G(-s_)
+            torch._foreach_sub_(gp, gm)
+            torch._foreach_add_(total, gp, alpha=-scale * w_)
+            del gp, gm
     for p, t in zip(params, total):
         p.grad = t if p.grad is None else p.grad + t
     return loss.detach(), E.detach(), F.detach()
