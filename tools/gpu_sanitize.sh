@@ -6,7 +6,7 @@
 # Logs land in gpurun_out/sanitizer_<tool>.txt (copy the summaries to profiles/).
 set -u
 mkdir -p gpurun_out
-SEL='(golden_forward_backward and (cfg1 or yaml_l2 or l3_trunc or norms_l3 or eu_mlp-)) or attention_dropout or cfg2_width or (head_energy_forces_golden and l2) or dipole_and_spatial or (gemm_layouts and (257 or 1000)) or fp16_split'
+SEL='(golden_forward_backward and (cfg1 or yaml_l2 or l3_trunc or norms_l3 or eu_mlp- or eu_linw_ln_ev or eu_linwa_postln_gated or eu_mlpa_edgeln)) or attention_dropout or cfg2_width or (head_energy_forces_golden and l2) or dipole_and_spatial or (gemm_layouts and (257 or 1000)) or fp16_split'
 TOOLS=${1:-"memcheck racecheck racecheck1cta synccheck initcheck"}
 for tool in $TOOLS; do
   extra=""
