@@ -44,6 +44,9 @@ struct Params {
   int add_vec, c_vec, act_vec;
   int red_add;            // add_src == C: accumulate into C with a TMA reduction store
   int act_tma;            // SiLU side output through a second TMA store (tmAct)
+  int a_tmem;             // K-major A: the converter writes the hi / lo tiles into TENSOR MEMORY (tcgen05.st) and the MMAs take
+                          // A from there: no converted-A write to and no A read from shared memory (the short-K GEMMs are
+                          // shared-memory-pipe bound).  TMEM: columns [0, 256) one accumulator stage, [256 + 64 s, ..) A stage s
   int dbg;                // GOTEN_GEMM_DBG (timing experiments only, results are wrong: 4 skip the operand split, 8 skip the output stores)
   float* partial;
   float* colsum;
@@ -150,7 +153,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const int split = w / n_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-        const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
+        const bool a_tm = !A_ROWS_ARE_K && p.a_tmem;
+        const bool one_acc = a_tm && BN > 192;   // 2 x 256 accumulator columns + the A stages exceed the 512 TMEM columns
+        const uint32_t acc = one_acc ? 0u : (tile_it & 1), aph = one_acc ? (tile_it & 1) : ((tile_it >> 1) & 1);
         mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)BN;
@@ -165,7 +170,19 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t a_hi = make_desc(sa + kk * 32, 16, 1024, 2), a_lo = make_desc(sal + kk * 32, 16, 1024, 2);
             const uint64_t b_hi = make_desc(sbh + kk * 32, 16, 1024, 2), b_lo = make_desc(sbl + kk * 32, 16, 1024, 2);
-            if (NCTA == 2) {
+            if (a_tm) {
+              // 192-column tiles: two accumulator stages in columns [0, 384) and a TWO-deep A ring behind them
+              const uint32_t ta_hi = tmem_base + (BN == 192 ? 384 + (it & 1) * 64 : 256 + s * 64) + kk * 8, ta_lo = ta_hi + 32;
+              if (NCTA == 2) {
+                umma_f16_ts_2cta(d_tmem, ta_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                umma_f16_ts_2cta(d_tmem, ta_hi, b_lo, idesc, 1u);
+                umma_f16_ts_2cta(d_tmem, ta_hi, b_hi, idesc, 1u);
+              } else {
+                umma_f16_ts(d_tmem, ta_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+                umma_f16_ts(d_tmem, ta_hi, b_lo, idesc, 1u);
+                umma_f16_ts(d_tmem, ta_hi, b_hi, idesc, 1u);
+              }
+            } else if (NCTA == 2) {
               umma_f16_2cta(d_tmem, a_lo, b_hi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
               umma_f16_2cta(d_tmem, a_hi, b_lo, idesc, 1u);
               umma_f16_2cta(d_tmem, a_hi, b_hi, idesc, 1u);
@@ -182,7 +199,10 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else if (warp >= CONV_WARP0) {
     // =============================== converter ==================================
-    const int ct = threadIdx.x - CONV_WARP0 * 32;  // 0..127 = tile row (M index) this thread produces
+    const bool a_tm = !A_ROWS_ARE_K && p.a_tmem;
+    // 0..127 = tile row (M index) this thread produces; with A in tensor memory the row must sit in the TMEM lane
+    // quadrant the warp may access (warp id mod 4)
+    const int ct = a_tm ? (warp & 3) * 32 + lane : threadIdx.x - CONV_WARP0 * 32;
     const float sA = scale_of(*p.amax_a);
     const float sB = scale_of(*p.amax_b);
     const uint32_t sw = (uint32_t)(ct & 7);
@@ -208,6 +228,29 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
           for (int c = 0; c < 16; ++c)
             v[c] = *reinterpret_cast<const float4*>(a_raw + (c >> 3) * (A_BYTES / 2) + ct * 128 + ((((uint32_t)c & 7) ^ sw) << 4));
+          if (a_tm) {
+            uint32_t hw[32], lw[32];   // packed half pairs: word j = K elements 2j, 2j + 1 of this row
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+              split2(v[c].x * sA, v[c].y * sA, hw[2 * c], lw[2 * c]);
+              split2(v[c].z * sA, v[c].w * sA, hw[2 * c + 1], lw[2 * c + 1]);
+            }
+            uint32_t ta = tmem_base + 256 + s * 64 + ((uint32_t)((warp & 3) * 32) << 16);
+            if (BN == 192) {
+              // two-deep A ring: slot it & 1 is free once the MMAs of k-block it - 2 have completed, which is what the
+              // `empty` barrier of the shared-memory stage that k-block used reports
+              ta = tmem_base + 384 + (it & 1) * 64 + ((uint32_t)((warp & 3) * 32) << 16);
+              if (it >= 2) {
+                const uint32_t it2 = it - 2;
+                mbar_wait(bar_empty + 8 * (it2 % STAGES), (it2 / STAGES) & 1);
+                tc_fence_after();
+              }
+            }
+            GOTEN_STTM_X32(ta, hw);
+            GOTEN_STTM_X32(ta + 32, lw);
+            tmem_wait_st();
+            tc_fence_before();
+          } else {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {  // 16 B chunk of 8 halves = floats 8c .. 8c+7
             uint4 h, l;
@@ -218,6 +261,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const uint32_t off = (((uint32_t)c ^ sw) << 4);
             *reinterpret_cast<uint4*>(hi_row + off) = h;
             *reinterpret_cast<uint4*>(lo_row + off) = l;
+          }
           }
         } else {
           // thread = MN column ct of the raw [64 k][128 mn] tile: read the column, then (after every converter
@@ -285,7 +329,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else {
     // =============================== epilogue (umma.cuh) ========================
     gemm_epilogue<NCTA, BM, EPI_WARP0>(p, tmC, tmAct, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
-                                       n_tiles, BN, rank, inv_scale_of(*p.amax_a), inv_scale_of(*p.amax_b));
+                                       n_tiles, BN, rank, inv_scale_of(*p.amax_a), inv_scale_of(*p.amax_b),
+                                       (!A_ROWS_ARE_K && p.a_tmem && BN > 192) ? 1 : 2);
   }
 
   tc_fence_before();
@@ -508,6 +553,12 @@ static Tc16Plan tc16_plan(int M, int N, int K, int trans_a, int trans_b) {
   t.a_rows_are_k = trans_a != 0;
   if (t.a_rows_are_k && M % 32 != 0) return t;  // split-K partial stores are whole 32-row blocks
   t.block_n = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  {
+    static int force_bn = -1;   // GOTEN_GEMM_BN=128: narrower tiles (timing experiments)
+    if (force_bn < 0) { const char* e = getenv("GOTEN_GEMM_BN"); force_bn = e ? atoi(e) : 0; }
+    if (force_bn == 128 && t.block_n == 256) t.block_n = 128;
+    if (force_bn == 192 && t.block_n == 256 && N >= 512) t.block_n = 192;
+  }
   static int force_ncta = -1;
   if (force_ncta < 0) { const char* e = getenv("GOTEN_GEMM_NCTA"); force_ncta = e ? atoi(e) : 0; }
   t.ncta = (force_ncta == 1) ? 1 : ((M >= 256 || force_ncta == 2) ? 2 : 1);
@@ -667,6 +718,11 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   p.act_out = act_out; p.ld_act = ld_act; p.act_lo = act_lo; p.act_hi = act_hi;
   p.red_add = red_add ? 1 : 0;
   p.act_tma = act_tma ? 1 : 0;
+  {
+    static int atm = -1;   // GOTEN_GEMM_ATMEM=1: A operand through tensor memory (K-major A only)
+    if (atm < 0) { const char* e = getenv("GOTEN_GEMM_ATMEM"); atm = e ? atoi(e) : 0; }
+    p.a_tmem = (atm && !t.a_rows_are_k) ? 1 : 0;
+  }
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("GOTEN_GEMM_DBG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   p.add_vec = (add_src != nullptr && aligned16(add_src) && ld_add % 4 == 0) ? 1 : 0;
   p.c_vec = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;

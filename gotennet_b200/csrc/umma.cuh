@@ -193,6 +193,39 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, u
       : "memory");
 }
 __device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// A operand from tensor memory (lane = row of A, 32-bit column j = K elements 2j, 2j + 1), B from a shared-memory descriptor
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ts_2cta(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// registers -> 32 consecutive 32-bit columns of this thread's TMEM lane; complete after tmem_wait_st()
+#define GOTEN_STTM_X32(taddr, r)                                                                                      \
+  asm volatile(                                                                                                       \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                 \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                                      \
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"                              \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),  \
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),    \
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),   \
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                    \
+      : "memory")
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -339,7 +372,7 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
                                               uint32_t bar_tfull,
                                               uint32_t bar_tempty, uint32_t tmem_base, int warp, int lane, int unit,
                                               int n_units, int n_items, int n_tiles, int BN, uint32_t rank, float un_a,
-                                              float un_b) {
+                                              float un_b, int acc_stages = 2) {
   // =============================== epilogue ===================================
   // The four warps were the slowest stage of the short-K GEMMs (ncu source view, round 2: busy 87 % of the time, one
   // warp per scheduler running a serial chain tcgen05.ld -> bias LDG -> generic ST -> fence -> TMA per 32-column
@@ -358,7 +391,8 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
   for (int w = unit; w < n_items; w += n_units, ++tile_it) {
     const int split = w / n_tiles, tile = w % n_tiles;
     const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN;
-    const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
+    // two accumulator stages alternate; with one (A operand resident in tensor memory) its barrier flips every tile
+    const uint32_t acc = acc_stages == 2 ? (tile_it & 1) : 0u, aph = acc_stages == 2 ? ((tile_it >> 1) & 1) : (tile_it & 1);
     const int row_base = m0 + q * 32;
     const bool rows_live = row_base < p.M;
     const int nch = rows_live ? min(BN, p.N - n0 + 31) / 32 : 0;   // 32-column chunks with a live column

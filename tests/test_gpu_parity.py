@@ -136,6 +136,36 @@ def test_gemm_layouts(g, dev, M, N, K, impl):
     assert rel(out2, wide[:, K:2 * K].double().cpu() @ w.double().T) < tol
 
 
+def test_gemm_a_operand_in_tensor_memory(dev):
+    """GOTEN_GEMM_ATMEM=1 (opt-in form of the split-fp16 GEMM: the converter writes the A tiles with tcgen05.st and the
+    MMAs read A from tensor memory; one accumulator stage for 256-column tiles, two for narrower ones): same results as
+    the default form.  The switch is read once per process, hence the child process."""
+    import subprocess
+    import sys
+    code = (
+        "import torch\n"
+        "from gotennet_b200 import ops\n"
+        "dev = torch.device('cuda:0')\n"
+        "for M, N, K in ((1000, 256, 320), (4096, 1792, 256), (777, 96, 1024), (300, 512, 64)):\n"
+        "    g = torch.Generator().manual_seed(M)\n"
+        "    a = torch.randn(M, K, generator=g); w = torch.randn(N, K, generator=g); b = torch.randn(N, generator=g)\n"
+        "    out = torch.empty(M, N, device=dev)\n"
+        "    ops.gemm(a.to(dev), K, 0, w.to(dev), K, 1, out, N, M, N, K, bias=b.to(dev), impl=3)\n"
+        "    ref = a.double() @ w.double().T + b.double()\n"
+        "    err = ((out.cpu().double() - ref).abs().max() / ref.abs().max()).item()\n"
+        "    assert err < 2e-5, (M, N, K, err)\n"
+        "    gr = torch.randn(M, N, generator=g); da = torch.empty(M, K, device=dev)\n"
+        "    ops.gemm(gr.to(dev), N, 0, w.to(dev), K, 0, da, K, M, K, N, impl=3)\n"
+        "    ref = gr.double() @ w.double()\n"
+        "    err = ((da.cpu().double() - ref).abs().max() / ref.abs().max()).item()\n"
+        "    assert err < 2e-5, (M, N, K, err)\n"
+        "print('ok')\n")
+    env = dict(os.environ, GOTEN_GEMM_ATMEM="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout + r.stderr
+
+
 def test_gemm_fp16_split_dynamic_range(g, dev):
     """Split-fp16 arm: per-tensor power-of-two scaling keeps fp32-class accuracy for tiny gradients, for a few
     huge outliers inside a tensor, and with caller-supplied (loose) operand bounds; goten_absmax is exact."""
