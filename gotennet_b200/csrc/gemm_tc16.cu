@@ -416,6 +416,187 @@ __global__ void split16_rows_kernel(const float* __restrict__ in, int ld, int ro
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Panel form for the short-K forward GEMMs (K <= 256, K-major A, weights pre-split, CTA pairs): A-STATIONARY.
+// The converted A operand of a whole M block (256 rows x K <= 256: 128 lanes x 256 TMEM columns per CTA, hi + lo) is
+// written ONCE into tensor memory and reused by every 128-column tile of the block, so per tile only the weight tiles
+// cross shared memory: the default kernel re-stages and re-splits A for each column tile and is bound by the SM's
+// shared-memory pipe.  TMEM: columns [0, 256) two 128-column accumulator stages, [256, 512) the panel.
+// Shared memory: 4 raw A stages (one per k-block of the NEXT block, loaded while the current one is computed), a
+// 4-deep ring of weight stages (hi + lo, 16 KB), the epilogue staging blocks.
+//   warp 0   TMA producer (weights of the current block; raw A of the next block after the first tile's weights)
+//   warp 1   leader CTA: MMA issuer ([d_tmem], [a_tmem], b_desc form); peer CTA: relays "my weight stage has landed"
+//   warps 2-5 epilogue (umma.cuh, panel order)     warps 6-9 converter: raw A -> hi / lo -> tcgen05.st into the panel
+constexpr int P_AR = 4, P_BS = 4, P_BN = 128, P_BNH = 64;
+constexpr uint32_t P_B_BYTES = (uint32_t)P_BNH * BK * 2;   // one fp16 weight tile (hi or lo) of this CTA: 8 KB
+constexpr uint32_t P_BSTAGE = 2 * P_B_BYTES;
+constexpr int P_NBARS = 4 * P_AR + 3 * P_BS + 1 + 4;       // a_full, a_empty | b_full, b_empty, b_peer | pready[4] .. see below
+constexpr size_t P_SMEM = 1024 + (size_t)P_AR * A_BYTES + (size_t)P_BS * P_BSTAGE + 4 * 2 * 4096 + 40 * 8 + 16;
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm16_panel_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
+                    const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
+                    const __grid_constant__ CUtensorMap tmAct, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_smem = smem;
+  uint8_t* b_smem = smem + (size_t)P_AR * A_BYTES;
+  uint8_t* epi_smem = b_smem + (size_t)P_BS * P_BSTAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + 4 * 2 * 4096);
+  const uint32_t bar_afull = smem_u32(bars), bar_aempty = bar_afull + 8 * P_AR;
+  const uint32_t bar_bfull = bar_aempty + 8 * P_AR, bar_bempty = bar_bfull + 8 * P_BS, bar_bpeer = bar_bempty + 8 * P_BS;
+  const uint32_t bar_pready = bar_bpeer + 8 * P_BS, bar_pfree = bar_pready + 8 * 4;
+  const uint32_t bar_tfull = bar_pfree + 8, bar_tempty = bar_tfull + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 36);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int unit = (int)(blockIdx.x >> 1), n_units = (int)(gridDim.x >> 1);
+  const int KB = p.kb_total;   // <= 4
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < P_AR; ++s) { mbar_init(bar_afull + 8 * s, 1); mbar_init(bar_aempty + 8 * s, 4); }
+    for (int s = 0; s < P_BS; ++s) { mbar_init(bar_bfull + 8 * s, 1); mbar_init(bar_bempty + 8 * s, 1); mbar_init(bar_bpeer + 8 * s, 1); }
+    for (int k = 0; k < 4; ++k) mbar_init(bar_pready + 8 * k, 8);   // four converter warps of both CTAs
+    mbar_init(bar_pfree, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(bar_tfull + 8 * a, 1); mbar_init(bar_tempty + 8 * a, 8); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      uint32_t ait = 0, bit = 0;
+      auto load_a = [&](int mb) {
+        const int m0 = mb * (BM * 2) + (int)rank * BM;
+        for (int kb = 0; kb < KB; ++kb, ++ait) {
+          const uint32_t s = ait % P_AR, ph = (ait / P_AR) & 1;
+          mbar_wait(bar_aempty + 8 * s, ph ^ 1);
+          const uint32_t sa = smem_u32(a_smem + (size_t)s * A_BYTES), bar = bar_afull + 8 * s;
+          mbar_arrive_expect_tx(bar, A_BYTES);
+          tma_load_2d(sa, &tmA, bar, kb * BK, m0);
+          tma_load_2d(sa + A_BYTES / 2, &tmA, bar, kb * BK + 32, m0);
+        }
+      };
+      if (unit < p.n_mt) load_a(unit);
+      for (int mb = unit; mb < p.n_mt; mb += n_units) {
+        for (int nt = 0; nt < p.n_nt; ++nt) {
+          const int n0 = nt * P_BN + (int)rank * P_BNH;
+          for (int kb = 0; kb < KB; ++kb, ++bit) {
+            const uint32_t s = bit % P_BS, ph = (bit / P_BS) & 1;
+            mbar_wait(bar_bempty + 8 * s, ph ^ 1);
+            const uint32_t sb = smem_u32(b_smem + (size_t)s * P_BSTAGE), bar = bar_bfull + 8 * s;
+            mbar_arrive_expect_tx(bar, P_BSTAGE);
+            tma_load_2d(sb, &tmBh, bar, kb * BK, n0);
+            tma_load_2d(sb + P_B_BYTES, &tmBl, bar, kb * BK, n0);
+          }
+          // the raw A tiles of the NEXT block: their stages were released while this block's panel was written
+          if (nt == 0 && mb + n_units < p.n_mt) load_a(mb + n_units);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && rank == 0) {
+      // =============================== MMA issuer =================================
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)((BM * 2) >> 4) << 24);
+      uint32_t bit = 0, tile_it = 0, mbi = 0;
+      for (int mb = unit; mb < p.n_mt; mb += n_units, ++mbi) {
+        for (int nt = 0; nt < p.n_nt; ++nt, ++tile_it) {
+          const uint32_t acc = tile_it & 1, aph = (tile_it >> 1) & 1;
+          mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * (uint32_t)P_BN;
+          for (int kb = 0; kb < KB; ++kb, ++bit) {
+            if (nt == 0) mbar_wait(bar_pready + 8 * kb, mbi & 1);
+            const uint32_t s = bit % P_BS, ph = (bit / P_BS) & 1;
+            mbar_wait(bar_bfull + 8 * s, ph);
+            mbar_wait(bar_bpeer + 8 * s, ph);
+            tc_fence_after();
+            const uint32_t sbh = smem_u32(b_smem + (size_t)s * P_BSTAGE), sbl = sbh + P_B_BYTES;
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t b_hi = make_desc(sbh + kk * 32, 16, 1024, 2), b_lo = make_desc(sbl + kk * 32, 16, 1024, 2);
+              const uint32_t ta_hi = tmem_base + 256 + kb * 64 + kk * 8, ta_lo = ta_hi + 32;
+              umma_f16_ts_2cta(d_tmem, ta_lo, b_hi, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+              umma_f16_ts_2cta(d_tmem, ta_hi, b_lo, idesc, 1u);
+              umma_f16_ts_2cta(d_tmem, ta_hi, b_hi, idesc, 1u);
+            }
+            umma_commit_2cta(bar_bempty + 8 * s);
+          }
+          umma_commit_2cta(bar_tfull + 8 * acc);
+        }
+        umma_commit_2cta(bar_pfree);   // every MMA that reads this block's panel has completed
+      }
+    } else if (lane == 0) {
+      // peer CTA: the leader's `full` barrier counts only the leader's own TMA bytes - report each landed stage
+      uint32_t bit = 0;
+      for (int mb = unit; mb < p.n_mt; mb += n_units)
+        for (int i = 0; i < p.n_nt * KB; ++i, ++bit) {
+          const uint32_t s = bit % P_BS, ph = (bit / P_BS) & 1;
+          mbar_wait(bar_bfull + 8 * s, ph);
+          mbar_arrive_cluster(bar_bpeer + 8 * s, 0);
+        }
+    }
+  } else if (warp >= CONV_WARP0) {
+    // =============================== converter ==================================
+    const int ct = (warp & 3) * 32 + lane;   // tile row = TMEM lane (the warp's lane quadrant)
+    const uint32_t sw = (uint32_t)(ct & 7);
+    const float sA = scale_of(*p.amax_a);
+    uint32_t ait = 0, mbi = 0;
+    for (int mb = unit; mb < p.n_mt; mb += n_units, ++mbi) {
+      if (mbi > 0) {   // the panel is free once the previous block's last MMA has completed
+        mbar_wait(bar_pfree, (mbi - 1) & 1);
+        tc_fence_after();
+      }
+      for (int kb = 0; kb < KB; ++kb, ++ait) {
+        const uint32_t s = ait % P_AR, ph = (ait / P_AR) & 1;
+        mbar_wait(bar_afull + 8 * s, ph);
+        const uint32_t a_raw = smem_u32(a_smem + (size_t)s * A_BYTES);
+        float4 v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = lds128(a_raw + (c >> 3) * (A_BYTES / 2) + ct * 128 + ((((uint32_t)c & 7) ^ sw) << 4));
+        uint32_t hw[32], lw[32];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          split2(v[c].x * sA, v[c].y * sA, hw[2 * c], lw[2 * c]);
+          split2(v[c].z * sA, v[c].w * sA, hw[2 * c + 1], lw[2 * c + 1]);
+        }
+        const uint32_t ta = tmem_base + 256 + kb * 64 + ((uint32_t)((warp & 3) * 32) << 16);
+        GOTEN_STTM_X32(ta, hw);
+        GOTEN_STTM_X32(ta + 32, lw);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(bar_aempty + 8 * s);               // raw stage consumed (this CTA's producer)
+          mbar_arrive_cluster(bar_pready + 8 * kb, 0);   // panel k-block written (leader's MMA issuer)
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue (umma.cuh) ========================
+    gemm_epilogue<2, BM, EPI_WARP0>(p, tmC, tmAct, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, 0, 0,
+                                    P_BN, rank, inv_scale_of(*p.amax_a), inv_scale_of(*p.amax_b), 2, true);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+  }
+}
+
 // B[K][N] (ld) -> fp16 hi / lo [N][Kp] through a 64 x 64 shared-memory tile (coalesced on both sides)
 __global__ void __launch_bounds__(256)
 split16_transpose_kernel(const float* __restrict__ in, int ld, int rows /*K*/, int cols /*N*/, int Kp,
@@ -538,6 +719,7 @@ struct Tc16Plan {
   bool a_rows_are_k;     // weight-gradient form: A given as [R][M]
   int block_n, n_mt, n_nt, splits, kb_total, kb_per_split;
   int ncta, stages;
+  bool panel;            // A-stationary panel kernel (short K, several column tiles)
   bool b_raw;            // weight-gradient form with B staged raw and converted in the kernel
   int64_t kp;            // padded K of the pre-split B copies (multiple of 8 halves = 16 B)
   int64_t b_bytes;       // bytes of each pre-split B copy
@@ -583,6 +765,19 @@ static Tc16Plan tc16_plan(int M, int N, int K, int trans_a, int trans_b) {
   }
   t.kb_per_split = (t.kb_total + t.splits - 1) / t.splits;
   t.splits = (t.kb_total + t.kb_per_split - 1) / t.kb_per_split;
+  {
+    // A-stationary panel kernel: K-major A with K <= 256 (the converted A of an M block fills the 256 spare TMEM
+    // columns), at least two 128-column tiles to reuse it, CTA pairs.  GOTEN_GEMM_PANEL=0|1 forces it off / on.
+    static int panel = -1;
+    if (panel < 0) { const char* e = getenv("GOTEN_GEMM_PANEL"); panel = e ? atoi(e) : 0; }
+    t.panel = panel && !t.a_rows_are_k && t.kb_total <= 4 && N >= 256 && M >= 512 && t.ncta == 2;
+    if (t.panel) {
+      t.block_n = tc16::P_BN;
+      t.n_nt = (N + t.block_n - 1) / t.block_n;
+      t.splits = 1;
+      t.kb_per_split = t.kb_total;
+    }
+  }
   t.kp = ((int64_t)K + 7) & ~int64_t(7);
   // Weight-gradient form with a single row of M tiles: every B tile is consumed exactly once, so the kernel converts
   // it in place (no pre-split copy through HBM).  With several M tiles the kernel is shared-memory-bandwidth bound and
@@ -731,10 +926,11 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   p.amax_a = pa; p.amax_b = pb;
   if (t.splits > 1) { p.bias = nullptr; p.add_src = nullptr; p.act_out = nullptr; }
 
-  const size_t smem = 1024 + (size_t)t.stages * (tc16::A_BYTES + 2 * (size_t)(t.block_n / t.ncta) * tc16::BK * 2) +
-                      4 * 2 * 4096 + (3 * tc16::MAX_STAGES + 4) * 8 + 16;
+  const size_t smem = t.panel ? tc16::P_SMEM
+                              : 1024 + (size_t)t.stages * (tc16::A_BYTES + 2 * (size_t)(t.block_n / t.ncta) * tc16::BK * 2) +
+                                    4 * 2 * 4096 + (3 * tc16::MAX_STAGES + 4) * 8 + 16;
   GOTEN_REQUIRE((int)smem <= smem_optin, "tcgen05 fp16 GEMM needs %zu B of shared memory", smem);
-  const int n_items = t.n_mt * t.n_nt * t.splits;
+  const int n_items = t.panel ? t.n_mt : t.n_mt * t.n_nt * t.splits;   // panel kernel: a work item is an M block
   const int max_units = sm_count / t.ncta;
   const int grid = (n_items < max_units ? n_items : max_units) * t.ncta;
   cudaLaunchConfig_t cfg{};
@@ -759,7 +955,15 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     }                                                                                                       \
     GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, mAct, p));                                     \
   } while (0)
-  if (t.b_raw) {
+  if (t.panel) {
+    auto k = tc16::gemm16_panel_kernel;
+    static int smem_set_p = 0;
+    if (!smem_set_p) {
+      GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+      smem_set_p = 1;
+    }
+    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, mAct, p));
+  } else if (t.b_raw) {
     if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, true, 2); else GOTEN_TC16_LAUNCH(true, true, 1);
   } else if (t.a_rows_are_k) {
     if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, false, 2); else GOTEN_TC16_LAUNCH(true, false, 1);

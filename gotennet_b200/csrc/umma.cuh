@@ -272,6 +272,33 @@ __device__ __forceinline__ void epilogue_block(const P& p, const CUtensorMap& tm
     __syncwarp();
   }
   const int l0 = ch * 4;
+  const bool has_bias = p.bias != nullptr && !p.partial;
+  if (!has_bias) {
+    // (no bias: data / weight gradients, split-K partials) un-scale only
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 v;
+      v.x = __uint_as_float(r[4 * c + 0]) * un; v.y = __uint_as_float(r[4 * c + 1]) * un;
+      v.z = __uint_as_float(r[4 * c + 2]) * un; v.w = __uint_as_float(r[4 * c + 3]) * un;
+      sts128(buf + lane * 128 + ((c ^ (lane & 7)) << 4), v);
+    }
+  } else if (nc0 + 32 <= p.N && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
+    // the 32 bias values of the chunk are the same for every lane: eight broadcast 16-byte loads (one L1 sector each),
+    // all issued before the first use - the 32 dependent SHFL -> FFMA pairs of the register-distributed form were the
+    // epilogue warps' main stall (ncu source view, round 2).  (Hoisting these loads above the tcgen05.wait::ld of the
+    // chunk was measured too: the eight live float4 spill, and every shape got 10 % slower; staging the tile's bias in
+    // shared memory - two named barriers per tile among the four warps, LDS.128 broadcasts - cost 6 %.)
+    float4 bq[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) bq[c] = __ldg(reinterpret_cast<const float4*>(p.bias + nc0) + c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float4 v;
+      v.x = fmaf(__uint_as_float(r[4 * c + 0]), un, bq[c].x); v.y = fmaf(__uint_as_float(r[4 * c + 1]), un, bq[c].y);
+      v.z = fmaf(__uint_as_float(r[4 * c + 2]), un, bq[c].z); v.w = fmaf(__uint_as_float(r[4 * c + 3]), un, bq[c].w);
+      sts128(buf + lane * 128 + ((c ^ (lane & 7)) << 4), v);
+    }
+  } else {
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     float4 v;
@@ -280,6 +307,7 @@ __device__ __forceinline__ void epilogue_block(const P& p, const CUtensorMap& tm
     v.z = fmaf(__uint_as_float(r[4 * c + 2]), un, __shfl_sync(0xffffffffu, blv[(4 * c + 2) & 7], l0 + (c >> 1)));
     v.w = fmaf(__uint_as_float(r[4 * c + 3]), un, __shfl_sync(0xffffffffu, blv[(4 * c + 3) & 7], l0 + (c >> 1)));
     sts128(buf + lane * 128 + ((c ^ (lane & 7)) << 4), v);
+  }
   }
   if (fast) {
     fence_proxy_async();
@@ -372,7 +400,7 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
                                               uint32_t bar_tfull,
                                               uint32_t bar_tempty, uint32_t tmem_base, int warp, int lane, int unit,
                                               int n_units, int n_items, int n_tiles, int BN, uint32_t rank, float un_a,
-                                              float un_b, int acc_stages = 2) {
+                                              float un_b, int acc_stages = 2, bool panel_order = false) {
   // =============================== epilogue ===================================
   // The four warps were the slowest stage of the short-K GEMMs (ncu source view, round 2: busy 87 % of the time, one
   // warp per scheduler running a serial chain tcgen05.ld -> bias LDG -> generic ST -> fence -> TMA per 32-column
@@ -388,9 +416,24 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
   const bool fast = (p.add_src == nullptr || p.red_add) && (p.act_out == nullptr || p.act_tma);
   const float un = un_a * un_b;
   uint32_t tile_it = 0, n_store = 0;
-  for (int w = unit; w < n_items; w += n_units, ++tile_it) {
-    const int split = w / n_tiles, tile = w % n_tiles;
-    const int m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM, n0 = (tile % p.n_nt) * BN;
+  // default order: work items unit, unit + n_units, ... over (split, M tile, N tile) with N fastest; panel order (the
+  // A-stationary kernel): M blocks unit, unit + n_units, ..., all N tiles of a block in turn
+  for (int w = unit;; ++tile_it) {
+    int split, m0, n0;
+    if (!panel_order) {
+      if (w >= n_items) break;
+      const int tile = w % n_tiles;
+      split = w / n_tiles;
+      m0 = (tile / p.n_nt) * (BM * NCTA) + (int)rank * BM;
+      n0 = (tile % p.n_nt) * BN;
+      w += n_units;
+    } else {
+      const int mb = unit + (int)(tile_it / (uint32_t)p.n_nt) * n_units;
+      if (mb >= p.n_mt) break;
+      split = 0;
+      m0 = mb * (BM * NCTA) + (int)rank * BM;
+      n0 = (int)(tile_it % (uint32_t)p.n_nt) * BN;
+    }
     // two accumulator stages alternate; with one (A operand resident in tensor memory) its barrier flips every tile
     const uint32_t acc = acc_stages == 2 ? (tile_it & 1) : 0u, aph = acc_stages == 2 ? ((tile_it >> 1) & 1) : (tile_it & 1);
     const int row_base = m0 + q * 32;
