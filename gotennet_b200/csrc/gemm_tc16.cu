@@ -6,7 +6,8 @@
 // (the reference runs its nn.Linear layers in strict fp32, scripts/train.py:16; three tf32 MMAs - gemm_tc.cu - cost
 //  two 16-bit MMA slots each, this form costs one each: same accuracy class at twice the tensor-pipe throughput).
 //
-// Structure (persistent, warp specialised, one CTA per SM, 320 threads) as in gemm_tc.cu:
+// Structure (persistent, warp specialised, one CTA per SM, 320 threads; 448 with eight epilogue warps for the
+// epilogue-bound short-K shapes, template parameter EPIW) as in gemm_tc.cu:
 //   warp 0      TMA producer: raw fp32 A tile + pre-split fp16 B_hi / B_lo tiles -> smem ring
 //   warp 1      TMEM allocator + MMA issuer: 12 x tcgen05.mma.kind::f16 (M128/256 x N<=256 x K16) per 64-deep k-block
 //   warps 2-5   epilogue: tcgen05.ld -> un-scale -> smem -> TMA store / fused bias + residual + SiLU side output
@@ -57,8 +58,10 @@ struct Params {
 
 // B_RAW (weight-gradient form only): B is staged as raw fp32 [64 k][BNH n] like A and converted in place by the
 // converter warps, so no pre-split copy of the (activation-sized) B operand is written to / re-read from HBM.
-template <bool A_ROWS_ARE_K, bool B_RAW, int NCTA>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// EPIW: epilogue warps (4, or 8 = two per TMEM lane quadrant for the epilogue-bound short-K shapes: 448 threads put four
+// warps on two of the SM's register-file partitions, i.e. 128 registers per thread instead of 168)
+template <bool A_ROWS_ARE_K, bool B_RAW, int NCTA, int EPIW = 4>
+__global__ void __launch_bounds__(64 + 32 * EPIW + 128, 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
               const __grid_constant__ CUtensorMap tmAct, const Params p) {
@@ -75,6 +78,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const uint32_t bar_full = smem_u32(bars), bar_conv = smem_u32(bars + MAX_STAGES), bar_empty = smem_u32(bars + 2 * MAX_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 3 * MAX_STAGES), bar_tempty = smem_u32(bars + 3 * MAX_STAGES + 2);
 
+  constexpr int CONV_WARP0 = EPI_WARP0 + EPIW;   // (shadows the 320-thread constant)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = NCTA == 2 ? cluster_ctarank() : 0u;
   const int unit = NCTA == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -88,7 +92,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4 * NCTA);
+      mbar_init(bar_tempty + 8 * a, EPIW * NCTA);
     }
     fence_barrier_init();
   }
@@ -328,7 +332,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   } else {
     // =============================== epilogue (umma.cuh) ========================
-    gemm_epilogue<NCTA, BM, EPI_WARP0>(p, tmC, tmAct, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
+    gemm_epilogue<NCTA, BM, EPI_WARP0, EPIW>(p, tmC, tmAct, epi_smem, bar_tfull, bar_tempty, tmem_base, warp, lane, unit, n_units, n_items,
                                        n_tiles, BN, rank, inv_scale_of(*p.amax_a), inv_scale_of(*p.amax_b),
                                        (!A_ROWS_ARE_K && p.a_tmem && BN > 192) ? 1 : 2);
   }
@@ -933,6 +937,15 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
   const int n_items = t.panel ? t.n_mt : t.n_mt * t.n_nt * t.splits;   // panel kernel: a work item is an M block
   const int max_units = sm_count / t.ncta;
   const int grid = (n_items < max_units ? n_items : max_units) * t.ncta;
+  // short-K K-major shapes are epilogue-bound: they run with eight epilogue warps (K <= GOTEN_GEMM_EPI8_K, default 512;
+  // GOTEN_GEMM_EPI8=0 switches the form off).  Measured, 4 -> 8 warps: edge projection 811 -> 779 us, node projections
+  // 44.3 -> 41.1 / 50.9 -> 47.2 / 64.7 -> 54.7 (SiLU side output), EQ|EK 83.6 -> 79.4; long K unchanged.
+  static int epi8_on = -1, epi8_k = 512;
+  if (epi8_on < 0) {
+    const char* e = getenv("GOTEN_GEMM_EPI8"); epi8_on = e ? atoi(e) : 1;
+    const char* k = getenv("GOTEN_GEMM_EPI8_K"); if (k) epi8_k = atoi(k);
+  }
+  const bool epi8 = epi8_on && !t.panel && !t.a_rows_are_k && !t.b_raw && K <= epi8_k && !p.a_tmem;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(tc16::NTHREADS);
@@ -967,6 +980,16 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, true, 2); else GOTEN_TC16_LAUNCH(true, true, 1);
   } else if (t.a_rows_are_k) {
     if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, false, 2); else GOTEN_TC16_LAUNCH(true, false, 1);
+  } else if (t.ncta == 2 && epi8) {
+    // eight epilogue warps (448 threads)
+    auto k = tc16::gemm16_kernel<false, false, 2, 8>;
+    static int smem_set8 = 0;
+    if (!smem_set8) {
+      GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin));
+      smem_set8 = 1;
+    }
+    cfg.blockDim = dim3(448);
+    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, mAct, p));
   } else {
     if (t.ncta == 2) GOTEN_TC16_LAUNCH(false, false, 2); else GOTEN_TC16_LAUNCH(false, false, 1);
   }

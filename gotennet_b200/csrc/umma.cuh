@@ -261,14 +261,16 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // One 32x32 block of the epilogue: registers (thread = row, 32 columns) -> un-scale + bias -> swizzled smem block ->
 // TMA store(s) (fast) or the row-wise register path with residual / SiLU side output.  `blv`: the tile's bias, lane l
 // holding columns n0 + 8 l .. 8 l + 7; column c of chunk ch sits in lane 4 ch + c / 8, slot c % 8.
-template <class P>
+template <int NBUF, class P>
 __device__ __forceinline__ void epilogue_block(const P& p, const CUtensorMap& tmC, const CUtensorMap& tmAct, const uint32_t (&r)[32],
                                                const float (&blv)[8], int ch, int nc0, int row_base, int split,
                                                uint32_t my_buf, uint32_t& n_store, int lane, float un, bool fast) {
   if (p.dbg & 8) return;
-  const uint32_t buf = my_buf + (n_store & 1) * 4096;
-  if (fast && n_store >= 2) {
-    if (lane == 0) bulk_wait_read<1>();
+  // NBUF staging blocks per warp (2: the TMA store of block k is read while block k + 1 is written; 1: the eight-warp
+  // form, where the second warp of the scheduler covers the wait)
+  const uint32_t buf = my_buf + (n_store % NBUF) * 4096;
+  if (fast && n_store >= (uint32_t)NBUF) {
+    if (lane == 0) bulk_wait_read<NBUF - 1>();
     __syncwarp();
   }
   const int l0 = ch * 4;
@@ -320,9 +322,9 @@ __device__ __forceinline__ void epilogue_block(const P& p, const CUtensorMap& tm
     }
     ++n_store;
     if (p.act_tma && nc0 >= p.act_lo && nc0 < p.act_hi) {   // warp-uniform: SiLU side output of this block
-      const uint32_t buf2 = my_buf + (n_store & 1) * 4096;
-      if (n_store >= 2) {
-        if (lane == 0) bulk_wait_read<1>();
+      const uint32_t buf2 = my_buf + (n_store % NBUF) * 4096;   // (NBUF = 1: rewritten in place once the store has read it)
+      if (n_store >= (uint32_t)NBUF) {
+        if (lane == 0) bulk_wait_read<NBUF - 1>();
         __syncwarp();
       }
 #pragma unroll
@@ -395,7 +397,7 @@ __device__ __forceinline__ void epilogue_block(const P& p, const CUtensorMap& tm
   __syncwarp();
 }
 
-template <int NCTA, int BM, int EPI_WARP0, class P>
+template <int NCTA, int BM, int EPI_WARP0, int EPIW = 4, class P>
 __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC, const CUtensorMap& tmAct, uint8_t* epi_smem,
                                               uint32_t bar_tfull,
                                               uint32_t bar_tempty, uint32_t tmem_base, int warp, int lane, int unit,
@@ -408,7 +410,11 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
   // while chunk ch is processed (two register buffers), the accumulator stage is handed back to the MMA warp as soon
   // as the last load has landed, and the staging block is written with st.shared.
   const int q = warp & 3;
-  const uint32_t my_buf = smem_u32(epi_smem) + (uint32_t)(warp - EPI_WARP0) * 2 * 4096;
+  // EPIW = 8: two warps per TMEM lane quadrant (warp % 4), the second set takes the odd 32-column chunks; the 32 KB of
+  // staging blocks then give one block per warp instead of two
+  constexpr int NBUF = EPIW == 4 ? 2 : 1, CST = EPIW / 4;
+  const int cs = (warp - EPI_WARP0) / 4;
+  const uint32_t my_buf = smem_u32(epi_smem) + (uint32_t)(warp - EPI_WARP0) * NBUF * 4096;
   // red_add: the residual already sits in C (add_src == C): the tile is ADDED to it by a TMA reduction store, so the
   // residual never passes through the SM (the register path moves 4 KB per warp and round trip)
   // act_tma: the SiLU side output (columns [act_lo, act_hi), act_lo a multiple of 32) leaves through a second TMA store of
@@ -468,17 +474,18 @@ __device__ __forceinline__ void gemm_epilogue(const P& p, const CUtensorMap& tmC
       }
       released = true;
     };
-    if (nch > 0) GOTEN_LDTM_X32(rA, tbase);
-    for (int ch = 0; ch < nch; ch += 2) {
+    if (cs < nch) GOTEN_LDTM_X32(rA, tbase + cs * 32);
+    for (int ch = cs; ch < nch; ch += 2 * CST) {
       tmem_wait_ld();
-      if (ch + 1 < nch) GOTEN_LDTM_X32(rB, tbase + (ch + 1) * 32);
+      if (ch + CST < nch) GOTEN_LDTM_X32(rB, tbase + (ch + CST) * 32);
       else release();
-      epilogue_block(p, tmC, tmAct, rA, blv, ch, n0 + ch * 32, row_base, split, my_buf, n_store, lane, un, fast);
-      if (ch + 1 < nch) {
+      epilogue_block<NBUF>(p, tmC, tmAct, rA, blv, ch, n0 + ch * 32, row_base, split, my_buf, n_store, lane, un, fast);
+      if (ch + CST < nch) {
         tmem_wait_ld();
-        if (ch + 2 < nch) GOTEN_LDTM_X32(rA, tbase + (ch + 2) * 32);
+        if (ch + 2 * CST < nch) GOTEN_LDTM_X32(rA, tbase + (ch + 2 * CST) * 32);
         else release();
-        epilogue_block(p, tmC, tmAct, rB, blv, ch + 1, n0 + (ch + 1) * 32, row_base, split, my_buf, n_store, lane, un, fast);
+        epilogue_block<NBUF>(p, tmC, tmAct, rB, blv, ch + CST, n0 + (ch + CST) * 32, row_base, split, my_buf, n_store, lane, un,
+                             fast);
       }
     }
     if (!released) release();
