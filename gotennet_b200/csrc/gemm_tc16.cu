@@ -222,8 +222,9 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1;
         mbar_wait(bar_full + 8 * s, ph);
         uint8_t* a_raw = smem + s * STAGE_BYTES;
-        uint8_t* hi_row = a_raw + ct * 128;
-        uint8_t* lo_row = hi_row + A_BYTES / 2;
+        // (explicit shared-space accesses: through the generic pointers the compiler emitted LD.E / ST.E)
+        const uint32_t a_raw_s = smem_u32(a_raw);
+        const uint32_t hi_row = a_raw_s + ct * 128, lo_row = hi_row + A_BYTES / 2;
         if (!A_ROWS_ARE_K && (p.dbg & 4)) {
         } else if (!A_ROWS_ARE_K) {
           // thread = tile row: its 64 floats live in row ct of the two raw boxes and are replaced by row ct of the
@@ -231,7 +232,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           float4 v[16];
 #pragma unroll
           for (int c = 0; c < 16; ++c)
-            v[c] = *reinterpret_cast<const float4*>(a_raw + (c >> 3) * (A_BYTES / 2) + ct * 128 + ((((uint32_t)c & 7) ^ sw) << 4));
+            v[c] = lds128(a_raw_s + (c >> 3) * (A_BYTES / 2) + ct * 128 + ((((uint32_t)c & 7) ^ sw) << 4));
           if (a_tm) {
             uint32_t hw[32], lw[32];   // packed half pairs: word j = K elements 2j, 2j + 1 of this row
 #pragma unroll
@@ -263,8 +264,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             split2(v[2 * c + 1].x * sA, v[2 * c + 1].y * sA, h.z, l.z);
             split2(v[2 * c + 1].z * sA, v[2 * c + 1].w * sA, h.w, l.w);
             const uint32_t off = (((uint32_t)c ^ sw) << 4);
-            *reinterpret_cast<uint4*>(hi_row + off) = h;
-            *reinterpret_cast<uint4*>(lo_row + off) = l;
+            sts128u(hi_row + off, h);
+            sts128u(lo_row + off, l);
           }
           }
         } else {
@@ -272,7 +273,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           // thread has read) write it as K-major row ct of the hi / lo tiles
           float v[BK];
 #pragma unroll
-          for (int k = 0; k < BK; ++k) v[k] = *reinterpret_cast<const float*>(a_raw + k * 512 + ct * 4);
+          for (int k = 0; k < BK; ++k) v[k] = lds32(a_raw_s + k * 512 + ct * 4);
           conv_bar_sync();
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -282,8 +283,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             split2(v[8 * c + 4] * sA, v[8 * c + 5] * sA, h.z, l.z);
             split2(v[8 * c + 6] * sA, v[8 * c + 7] * sA, h.w, l.w);
             const uint32_t off = (((uint32_t)c ^ sw) << 4);
-            *reinterpret_cast<uint4*>(hi_row + off) = h;
-            *reinterpret_cast<uint4*>(lo_row + off) = l;
+            sts128u(hi_row + off, h);
+            sts128u(lo_row + off, l);
           }
           if (do_cs) {
 #pragma unroll
@@ -291,16 +292,15 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
           if (B_RAW) {
             // same transposing split for column ct of the raw B tile (BNH <= 128 columns, row pitch BNH floats)
-            uint8_t* b_raw = a_raw + A_BYTES;
+            const uint32_t b_raw = a_raw_s + A_BYTES;
             const bool mine = ct < BNH;
             if (mine) {
 #pragma unroll
-              for (int k = 0; k < BK; ++k) v[k] = *reinterpret_cast<const float*>(b_raw + (size_t)k * BNH * 4 + ct * 4);
+              for (int k = 0; k < BK; ++k) v[k] = lds32(b_raw + (uint32_t)k * BNH * 4 + ct * 4);
             }
             conv_bar_sync();
             if (mine) {
-              uint8_t* bh_row = b_raw + ct * 128;
-              uint8_t* bl_row = bh_row + B_BYTES;
+              const uint32_t bh_row = b_raw + ct * 128, bl_row = bh_row + B_BYTES;
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
                 uint4 h, l;
@@ -309,8 +309,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                 split2(v[8 * c + 4] * sB, v[8 * c + 5] * sB, h.z, l.z);
                 split2(v[8 * c + 6] * sB, v[8 * c + 7] * sB, h.w, l.w);
                 const uint32_t off = (((uint32_t)c ^ sw) << 4);
-                *reinterpret_cast<uint4*>(bh_row + off) = h;
-                *reinterpret_cast<uint4*>(bl_row + off) = l;
+                sts128u(bh_row + off, h);
+                sts128u(bl_row + off, l);
               }
             }
           }
