@@ -268,7 +268,10 @@ __device__ __forceinline__ void gata_bwd_tgt_staged_body(
   float* s_al = part + (size_t)EC * S * n_grp;          // [max_deg][H]
   float* s_aux = s_al + (size_t)max_deg * H;            // [max_deg][H]
   // [2][S][blockDim]: per-thread d alpha~ partials of one edge (16 B aligned for the vector group sums)
-  float* s_pk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_aux + (size_t)max_deg * H) + 15) & ~uintptr_t(15));
+  // (offset arithmetic on the shared array, not an integer round trip of the pointer: the latter makes every access to
+  //  s_pk / s_geo a generic LD.E / ST.E instead of LDS / STS)
+  float* s_pk = reinterpret_cast<float*>(smem_raw) +
+                (((size_t)((s_aux + (size_t)max_deg * H) - reinterpret_cast<float*>(smem_raw)) + 3) & ~size_t(3));
   float* s_geo = s_pk + (size_t)2 * S * blockDim.x;      // GEO: [2][(1 + L)][blockDim + 4]
   const uint32_t bar0 = tma::smem_u32(bars);
   const uint32_t stage0 = tma::smem_u32(stages);
