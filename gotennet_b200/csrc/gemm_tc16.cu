@@ -60,8 +60,10 @@ struct Params {
 // converter warps, so no pre-split copy of the (activation-sized) B operand is written to / re-read from HBM.
 // EPIW: epilogue warps (4, or 8 = two per TMEM lane quadrant for the epilogue-bound short-K shapes: 448 threads put four
 // warps on two of the SM's register-file partitions, i.e. 128 registers per thread instead of 168)
-template <bool A_ROWS_ARE_K, bool B_RAW, int NCTA, int EPIW = 4>
-__global__ void __launch_bounds__(64 + 32 * EPIW + 128, 1)
+// CONVW: converter warps (4, or 8 for the weight-gradient forms: two threads per tile column, each transposing half of
+// the 64 k values - those kernels are bound by the converter's strided shared-memory reads, not by the epilogue)
+template <bool A_ROWS_ARE_K, bool B_RAW, int NCTA, int EPIW = 4, int CONVW = 4>
+__global__ void __launch_bounds__(64 + 32 * (EPIW + CONVW), 1)
 gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh,
               const __grid_constant__ CUtensorMap tmBl, const __grid_constant__ CUtensorMap tmC,
               const __grid_constant__ CUtensorMap tmAct, const Params p) {
@@ -87,7 +89,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_conv + 8 * s, 4 * NCTA);
+      mbar_init(bar_conv + 8 * s, CONVW * NCTA);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -137,6 +139,8 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           } else {
             // A[R][M]: one un-swizzled box of [64 k rows][128 floats]
             tma_load_2d(sa, &tmA, bar, m0, kb * BK);
+            // (measured: an L2 prefetch of this tile 4 / 8 / 16 k-blocks ahead, cp.async.bulk.prefetch.tensor, makes the
+            //  edge weight gradient 2 / 4 / 7 % slower - the ring is not waiting on DRAM latency)
           }
           if (B_RAW) {
             tma_load_2d(sbh, &tmBh, bar, n0, kb * BK);   // tmBh = fp32 map over B[R][N]: box [64 k][BNH n]
@@ -206,7 +210,12 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const bool a_tm = !A_ROWS_ARE_K && p.a_tmem;
     // 0..127 = tile row (M index) this thread produces; with A in tensor memory the row must sit in the TMEM lane
     // quadrant the warp may access (warp id mod 4)
-    const int ct = a_tm ? (warp & 3) * 32 + lane : threadIdx.x - CONV_WARP0 * 32;
+    static_assert(CONVW == 4 || (CONVW == 8 && A_ROWS_ARE_K), "eight converter warps: weight-gradient forms only");
+    constexpr int CF = CONVW / 4, KH = BK / CF, NCH = 8 / CF;   // threads per column, k values and 16 B chunks per thread
+    const int cidx = threadIdx.x - CONV_WARP0 * 32;
+    const int ct = a_tm ? (warp & 3) * 32 + lane : cidx % 128;
+    const int hf = cidx / 128;   // which half of the k range (0 with four warps)
+    __shared__ float cs_x[CONVW == 8 ? 128 : 1];   // column-sum hand-over between the two halves
     const float sA = scale_of(*p.amax_a);
     const float sB = scale_of(*p.amax_b);
     const uint32_t sw = (uint32_t)(ct & 7);
@@ -271,24 +280,24 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         } else {
           // thread = MN column ct of the raw [64 k][128 mn] tile: read the column, then (after every converter
           // thread has read) write it as K-major row ct of the hi / lo tiles
-          float v[BK];
+          float v[KH];
 #pragma unroll
-          for (int k = 0; k < BK; ++k) v[k] = lds32(a_raw_s + k * 512 + ct * 4);
-          conv_bar_sync();
+          for (int k = 0; k < KH; ++k) v[k] = lds32(a_raw_s + (hf * KH + k) * 512 + ct * 4);
+          conv_bar_sync<CONVW * 32>();
 #pragma unroll
-          for (int c = 0; c < 8; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             uint4 h, l;
             split2(v[8 * c + 0] * sA, v[8 * c + 1] * sA, h.x, l.x);
             split2(v[8 * c + 2] * sA, v[8 * c + 3] * sA, h.y, l.y);
             split2(v[8 * c + 4] * sA, v[8 * c + 5] * sA, h.z, l.z);
             split2(v[8 * c + 6] * sA, v[8 * c + 7] * sA, h.w, l.w);
-            const uint32_t off = (((uint32_t)c ^ sw) << 4);
+            const uint32_t off = (((uint32_t)(hf * NCH + c) ^ sw) << 4);
             sts128u(hi_row + off, h);
             sts128u(lo_row + off, l);
           }
           if (do_cs) {
 #pragma unroll
-            for (int k = 0; k < BK; ++k) csum += v[k];
+            for (int k = 0; k < KH; ++k) csum += v[k];
           }
           if (B_RAW) {
             // same transposing split for column ct of the raw B tile (BNH <= 128 columns, row pitch BNH floats)
@@ -296,19 +305,19 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const bool mine = ct < BNH;
             if (mine) {
 #pragma unroll
-              for (int k = 0; k < BK; ++k) v[k] = lds32(b_raw + (uint32_t)k * BNH * 4 + ct * 4);
+              for (int k = 0; k < KH; ++k) v[k] = lds32(b_raw + (uint32_t)(hf * KH + k) * BNH * 4 + ct * 4);
             }
-            conv_bar_sync();
+            conv_bar_sync<CONVW * 32>();
             if (mine) {
               const uint32_t bh_row = b_raw + ct * 128, bl_row = bh_row + B_BYTES;
 #pragma unroll
-              for (int c = 0; c < 8; ++c) {
+              for (int c = 0; c < NCH; ++c) {
                 uint4 h, l;
                 split2(v[8 * c + 0] * sB, v[8 * c + 1] * sB, h.x, l.x);
                 split2(v[8 * c + 2] * sB, v[8 * c + 3] * sB, h.y, l.y);
                 split2(v[8 * c + 4] * sB, v[8 * c + 5] * sB, h.z, l.z);
                 split2(v[8 * c + 6] * sB, v[8 * c + 7] * sB, h.w, l.w);
-                const uint32_t off = (((uint32_t)c ^ sw) << 4);
+                const uint32_t off = (((uint32_t)(hf * NCH + c) ^ sw) << 4);
                 sts128u(bh_row + off, h);
                 sts128u(bl_row + off, l);
               }
@@ -323,8 +332,14 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       }
       if (do_cs) {
+        if (CONVW == 8) {   // the two halves of the k range meet (uniform branch: do_cs depends on the tile only)
+          if (hf == 1) cs_x[ct] = csum;
+          conv_bar_sync<CONVW * 32>();
+          if (hf == 0) csum += cs_x[ct];
+          conv_bar_sync<CONVW * 32>();
+        }
         const int m = m0 + ct;
-        if (m < p.M) {
+        if (m < p.M && hf == 0) {
           if (p.partial_colsum) p.partial_colsum[(size_t)split * p.M + m] = csum;
           else p.colsum[m] = csum;
         }
@@ -945,6 +960,12 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
     const char* e = getenv("GOTEN_GEMM_EPI8"); epi8_on = e ? atoi(e) : 1;
     const char* k = getenv("GOTEN_GEMM_EPI8_K"); if (k) epi8_k = atoi(k);
   }
+  // eight converter warps for the weight-gradient form that converts BOTH operands in the kernel (b_raw: two
+  // transposing passes per k-block): 82 -> 77, 94 -> 83, 60 -> 54.5, 240 -> 182 us on the node-sized shapes; the forms
+  // with a pre-split B do not gain (GOTEN_GEMM_CONV8=0 off, =2 every weight-gradient form)
+  static int conv8_mode = -1;
+  if (conv8_mode < 0) { const char* e = getenv("GOTEN_GEMM_CONV8"); conv8_mode = e ? atoi(e) : 1; }
+  const bool conv8 = conv8_mode == 2 || (conv8_mode == 1 && t.b_raw);
   const bool epi8 = epi8_on && !t.panel && !t.a_rows_are_k && !t.b_raw && K <= epi8_k && !p.a_tmem;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
@@ -976,6 +997,21 @@ int gemm_tc16(const float* A, int lda, int trans_a, const float* B, int ldb, int
       smem_set_p = 1;
     }
     GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, mAct, p));
+  } else if (t.a_rows_are_k && t.ncta == 2 && conv8) {
+    // weight-gradient forms with eight converter warps (448 threads)
+#define GOTEN_TC16_LAUNCH8(BR)                                                                               \
+  do {                                                                                                      \
+    auto k = tc16::gemm16_kernel<true, BR, 2, 4, 8>;                                                         \
+    static int smem_set_c8 = 0;                                                                             \
+    if (!smem_set_c8) {                                                                                     \
+      GOTEN_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin - 1024)); /* 512 B static */ \
+      smem_set_c8 = 1;                                                                                      \
+    }                                                                                                       \
+    cfg.blockDim = dim3(448);                                                                               \
+    GOTEN_CHECK_CUDA(cudaLaunchKernelEx(&cfg, k, mA, mBh, mBl, mC, mAct, p));                               \
+  } while (0)
+    if (t.b_raw) GOTEN_TC16_LAUNCH8(true); else GOTEN_TC16_LAUNCH8(false);
+#undef GOTEN_TC16_LAUNCH8
   } else if (t.b_raw) {
     if (t.ncta == 2) GOTEN_TC16_LAUNCH(true, true, 2); else GOTEN_TC16_LAUNCH(true, true, 1);
   } else if (t.a_rows_are_k) {

@@ -192,7 +192,8 @@ __device__ __forceinline__ void umma_f16_2cta(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+template <int NT = 128>
+__device__ __forceinline__ void conv_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 // A operand from tensor memory (lane = row of A, 32-bit column j = K elements 2j, 2j + 1), B from a shared-memory descriptor
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
