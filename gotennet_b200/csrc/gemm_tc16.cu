@@ -277,6 +277,7 @@ gemm16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             sts128u(lo_row + off, l);
           }
           }
+        } else if (p.dbg & 4) {
         } else {
           // thread = MN column ct of the raw [64 k][128 mn] tile: read the column, then (after every converter
           // thread has read) write it as K-major row ct of the hi / lo tiles
