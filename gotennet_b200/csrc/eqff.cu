@@ -25,25 +25,28 @@ __device__ __forceinline__ void stv(float* __restrict__ p, const float* in) {
 
 template <int V>
 __global__ void eqff_ctx_fwd_kernel(const float* __restrict__ h, const float* __restrict__ P, int N, int C, int L,
-                                    float eps, float* __restrict__ ctx) {
+                                    float eps, float* __restrict__ ctx, float* __restrict__ ctx_amax) {
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-  if (idx >= (int64_t)N * C) return;
-  const int64_t n = idx / C;
-  const int c = (int)(idx % C);
-  float s[V], hv[V];
+  float amx = 0.f;   // running max |ctx| for the GEMM that consumes it (no separate absmax pass)
+  if (idx < (int64_t)N * C) {
+    const int64_t n = idx / C;
+    const int c = (int)(idx % C);
+    float s[V], hv[V];
 #pragma unroll
-  for (int q = 0; q < V; ++q) s[q] = 0.f;
-  for (int m = 0; m < L; ++m) {
-    float p[V];
-    ldv<V>(P + ((int64_t)m * N + n) * C + c, p);
+    for (int q = 0; q < V; ++q) s[q] = 0.f;
+    for (int m = 0; m < L; ++m) {
+      float p[V];
+      ldv<V>(P + ((int64_t)m * N + n) * C + c, p);
 #pragma unroll
-    for (int q = 0; q < V; ++q) s[q] = fmaf(p[q], p[q], s[q]);
+      for (int q = 0; q < V; ++q) s[q] = fmaf(p[q], p[q], s[q]);
+    }
+    ldv<V>(h + idx, hv);
+    stv<V>(ctx + n * 2 * C + c, hv);
+#pragma unroll
+    for (int q = 0; q < V; ++q) { s[q] = sqrtf(s[q] + eps); amx = fmaxf(amx, fmaxf(fabsf(hv[q]), s[q])); }
+    stv<V>(ctx + n * 2 * C + C + c, s);
   }
-  ldv<V>(h + idx, hv);
-  stv<V>(ctx + n * 2 * C + c, hv);
-#pragma unroll
-  for (int q = 0; q < V; ++q) s[q] = sqrtf(s[q] + eps);
-  stv<V>(ctx + n * 2 * C + C + c, s);
+  block_amax_commit(ctx_amax, amx);
 }
 
 template <int V>
@@ -74,25 +77,31 @@ __global__ void eqff_update_fwd_kernel(const float* __restrict__ h, const float*
 
 template <int V>
 __global__ void eqff_update_bwd_kernel(const float* __restrict__ g_h_out, const float* __restrict__ g_Xd_out,
-                                       const float* __restrict__ P, int N, int C, int L, float* __restrict__ g_m) {
+                                       const float* __restrict__ P, int N, int C, int L, float* __restrict__ g_m,
+                                       float* __restrict__ gm_amax) {
   const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
-  if (idx >= (int64_t)N * C) return;
-  const int64_t n = idx / C;
-  const int c = (int)(idx % C);
-  float s[V], g[V];
+  float amx = 0.f;
+  if (idx < (int64_t)N * C) {
+    const int64_t n = idx / C;
+    const int c = (int)(idx % C);
+    float s[V], g[V];
 #pragma unroll
-  for (int q = 0; q < V; ++q) s[q] = 0.f;
-  for (int m = 0; m < L; ++m) {
-    const int64_t o = ((int64_t)m * N + n) * C + c;
-    float gx[V], p[V];
-    ldv<V>(g_Xd_out + o, gx);
-    ldv<V>(P + o, p);
+    for (int q = 0; q < V; ++q) s[q] = 0.f;
+    for (int m = 0; m < L; ++m) {
+      const int64_t o = ((int64_t)m * N + n) * C + c;
+      float gx[V], p[V];
+      ldv<V>(g_Xd_out + o, gx);
+      ldv<V>(P + o, p);
 #pragma unroll
-    for (int q = 0; q < V; ++q) s[q] = fmaf(gx[q], p[q], s[q]);
+      for (int q = 0; q < V; ++q) s[q] = fmaf(gx[q], p[q], s[q]);
+    }
+    ldv<V>(g_h_out + idx, g);
+#pragma unroll
+    for (int q = 0; q < V; ++q) amx = fmaxf(amx, fmaxf(fabsf(g[q]), fabsf(s[q])));
+    stv<V>(g_m + n * 2 * C + c, g);
+    stv<V>(g_m + n * 2 * C + C + c, s);
   }
-  ldv<V>(g_h_out + idx, g);
-  stv<V>(g_m + n * 2 * C + c, g);
-  stv<V>(g_m + n * 2 * C + C + c, s);
+  block_amax_commit(gm_amax, amx);
 }
 
 template <int V>
@@ -143,9 +152,10 @@ extern "C" {
       KERNEL<1><<<(unsigned)cdiv64((int64_t)(N) * (C), 256), 256, 0, as_stream(stream)>>>(__VA_ARGS__); \
   } while (0)
 
-int goten_eqff_ctx_fwd(const float* h, const float* P, int N, int C, int L, float eps, float* ctx, void* stream) {
+int goten_eqff_ctx_fwd(const float* h, const float* P, int N, int C, int L, float eps, float* ctx, float* ctx_amax,
+                       void* stream) {
   if ((int64_t)N * C == 0) return 0;
-  EQFF_LAUNCH(eqff_ctx_fwd_kernel, N, C, h, P, N, C, L, eps, ctx);
+  EQFF_LAUNCH(eqff_ctx_fwd_kernel, N, C, h, P, N, C, L, eps, ctx, ctx_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }
@@ -157,9 +167,9 @@ int goten_eqff_update_fwd(const float* h, const float* Xd, const float* P, const
   return 0;
 }
 int goten_eqff_update_bwd(const float* g_h_out, const float* g_Xd_out, const float* P, int N, int C, int L,
-                          float* g_m, void* stream) {
+                          float* g_m, float* gm_amax, void* stream) {
   if ((int64_t)N * C == 0) return 0;
-  EQFF_LAUNCH(eqff_update_bwd_kernel, N, C, g_h_out, g_Xd_out, P, N, C, L, g_m);
+  EQFF_LAUNCH(eqff_update_bwd_kernel, N, C, g_h_out, g_Xd_out, P, N, C, L, g_m, gm_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

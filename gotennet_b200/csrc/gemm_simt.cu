@@ -252,12 +252,17 @@ int64_t gemm_simt_workspace_bytes(int M, int N, int K, int trans_a) {
 
 // ------------------------------------------------------------- small helpers
 __global__ void dsilu_mul_kernel(const float* __restrict__ g, int ldg, const float* __restrict__ pre, int ldp,
-                                 float* __restrict__ out, int ldo, int64_t M, int N) {
+                                 float* __restrict__ out, int ldo, int64_t M, int N, float* __restrict__ out_amax) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= M * N) return;
-  const int64_t m = idx / N;
-  const int n = (int)(idx % N);
-  out[m * ldo + n] = g[m * ldg + n] * dsiluf_(pre[m * ldp + n]);
+  float amx = 0.f;
+  if (idx < M * N) {
+    const int64_t m = idx / N;
+    const int n = (int)(idx % N);
+    const float v = g[m * ldg + n] * dsiluf_(pre[m * ldp + n]);
+    out[m * ldo + n] = v;
+    amx = fabsf(v);
+  }
+  block_amax_commit(out_amax, amx);
 }
 
 constexpr int CS_ROWS = 256;  // rows per partial block
@@ -400,9 +405,9 @@ int goten_gemm(const float* A, int lda, int trans_a, const float* B, int ldb, in
 }
 
 int goten_dsilu_mul(const float* g, int ldg, const float* pre, int ldp, float* out, int ldo, int64_t M, int N,
-                    void* stream) {
+                    float* out_amax, void* stream) {
   if (M * N == 0) return 0;
-  dsilu_mul_kernel<<<(unsigned)cdiv64(M * N, 256), 256, 0, as_stream(stream)>>>(g, ldg, pre, ldp, out, ldo, M, N);
+  dsilu_mul_kernel<<<(unsigned)cdiv64(M * N, 256), 256, 0, as_stream(stream)>>>(g, ldg, pre, ldp, out, ldo, M, N, out_amax);
   GOTEN_CHECK_LAUNCH();
   return 0;
 }

@@ -209,8 +209,10 @@ def linear_bwd(g, a, w, *, need_da=True, need_bias=True, add_src=None, am=None):
     return da, dw, db
 
 
-def dsilu_mul(g, ldg, g_off, pre, ldp, p_off, out, ldo, o_off, M, N):
-    lib().call("goten_dsilu_mul", _ptr(g, g_off), ldg, _ptr(pre, p_off), ldp, _ptr(out, o_off), ldo, M, N, _stream())
+def dsilu_mul(g, ldg, g_off, pre, ldp, p_off, out, ldo, o_off, M, N, out_amax=None):
+    """out = g * silu'(pre); out_amax (optional, zeroed 1-element device tensor): running max |out| for a consuming GEMM."""
+    lib().call("goten_dsilu_mul", _ptr(g, g_off), ldg, _ptr(pre, p_off), ldp, _ptr(out, o_off), ldo, M, N, _ptr(out_amax),
+               _stream())
 
 
 def permute_nlc(x, to_degree_major: bool):
@@ -721,7 +723,9 @@ class EqffBlockFn(torch.autograd.Function):
         P = torch.empty_like(Xd)
         gemm(Xd, C, 0, Wvu, C, 1, P, C, L * N, C, C, am=am)
         cx = torch.empty(N, 2 * C, device=dev)
-        L_.call("goten_eqff_ctx_fwd", _ptr(h), _ptr(P), N, C, L, float(eps), _ptr(cx), st)
+        cx_amax = am.slot(dev) if am.enabled else None   # written by the kernel that fills cx
+        am.put(cx, cx_amax)
+        L_.call("goten_eqff_ctx_fwd", _ptr(h), _ptr(P), N, C, L, float(eps), _ptr(cx), _ptr(cx_amax), st)
         Zm, Am = linear_fwd(cx, Wm1, bm1, act=True, am=am)
         M = linear_fwd(Am, Wm2, bm2, am=am)
         h2 = torch.empty_like(h)
@@ -746,10 +750,14 @@ class EqffBlockFn(torch.autograd.Function):
         g_h2 = g_h2.contiguous() if g_h2 is not None else torch.zeros(N, C, device=dev)
         g_Xd2 = g_Xd2.contiguous() if g_Xd2 is not None else torch.zeros(L, N, C, device=dev)
         g_M = torch.empty(N, 2 * C, device=dev)
-        L_.call("goten_eqff_update_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(P), N, C, L, _ptr(g_M), st)
+        gm_amax = am.slot(dev) if am.enabled else None
+        am.put(g_M, gm_amax)
+        L_.call("goten_eqff_update_bwd", _ptr(g_h2), _ptr(g_Xd2), _ptr(P), N, C, L, _ptr(g_M), _ptr(gm_amax), st)
         g_Am, dWm2, dbm2 = linear_bwd(g_M, Am, Wm2, am=am)
         g_Zm = torch.empty_like(g_Am)
-        dsilu_mul(g_Am, C, 0, Zm, C, 0, g_Zm, C, 0, N, C)
+        gzm_amax = am.slot(dev) if am.enabled else None
+        am.put(g_Zm, gzm_amax)
+        dsilu_mul(g_Am, C, 0, Zm, C, 0, g_Zm, C, 0, N, C, out_amax=gzm_amax)
         g_cx, dWm1, dbm1 = linear_bwd(g_Zm, cx, Wm1, am=am)
         g_P = torch.empty_like(P)
         g_h = torch.empty(N, C, device=dev)

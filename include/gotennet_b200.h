@@ -133,7 +133,7 @@ int goten_gemm_scaled(const float* A, int lda, int trans_a, const float* B, int 
                       int act_hi, float* colsum, const float* a_amax, const float* b_amax,
                       void* workspace, int64_t workspace_bytes, int impl, void* stream);
 /* Kernels that produce a large GEMM operand take an optional trailing `*_amax` DEVICE
- * pointer (t_amax, xd_amax, gze_amax, geq_amax, gek_amax, gp_amax): a running
+ * pointer (t_amax, xd_amax, gze_amax, geq_amax, gek_amax, gp_amax, ctx_amax, gm_amax, out_amax): a running
  * max |value written| (atomic max on a non-negative float the caller zeroed), so the
  * operand needs no separate goten_absmax pass.  NULL disables it.
  * out[0] = max(out[0], max |A[m][n]|) over a [M][N] matrix (ld = lda); out must hold a
@@ -145,7 +145,7 @@ int goten_absmax_multi(const float* const* ptrs, const int64_t* numel, int count
                        void* stream);
 /* out[m][n] = g[m][n] * silu'(pre[m][n])  (Dense activation backward, layers.py:527-528) */
 int goten_dsilu_mul(const float* g, int ldg, const float* pre, int ldp, float* out, int ldo,
-                    int64_t M, int N, void* stream);
+                    int64_t M, int N, float* out_amax, void* stream);
 /* column sums of a [M][N] matrix (bias gradients of non-fused cases) */
 int goten_colsum(const float* A, int lda, int64_t M, int N, float* out, float* workspace,
                  int64_t workspace_bytes, void* stream);
@@ -288,13 +288,13 @@ int goten_htr_bwd_src(const float* g_t_out, const float* EQ, const float* EK, in
  * EQFF.forward (gotennet.py:728-748). P = X W_vu^T comes from goten_gemm.
  * ctx[N][2C] = [ h | sqrt(sum_m P^2 + eps) ]                                   */
 int goten_eqff_ctx_fwd(const float* h, const float* P, int n_nodes, int C, int L, float eps,
-                       float* ctx, void* stream);
+                       float* ctx, float* ctx_amax, void* stream);
 /* h_out = h + m[:, :C];  Xd_out[m][n][c] = Xd + m[n][C+c] * P[m][n][c]  (m = gamma_m output, [N][2C]) */
 int goten_eqff_update_fwd(const float* h, const float* Xd, const float* P, const float* m,
                           int n_nodes, int C, int L, float* h_out, float* Xd_out, void* stream);
 /* g_m[N][2C] = [ g_h_out | sum_m g_Xd_out * P ] */
 int goten_eqff_update_bwd(const float* g_h_out, const float* g_Xd_out, const float* P, int n_nodes,
-                          int C, int L, float* g_m, void* stream);
+                          int C, int L, float* g_m, float* gm_amax, void* stream);
 /* g_P = g_Xd_out * m2 + g_ctx[:, C:] * P / n ;  g_h = g_h_out + g_ctx[:, :C]  (n = ctx[:, C:]) */
 int goten_eqff_ctx_bwd(const float* g_h_out, const float* g_Xd_out, const float* g_ctx,
                        const float* P, const float* m, const float* ctx, int n_nodes, int C, int L,
