@@ -78,6 +78,21 @@ def test_state_dict_matches_reference_module(g):
         assert all(a[k].shape == b[k].shape for k in a)
 
 
+def test_oracle_alias_expansion_of_the_gamma_w_network():
+    """W_edp is both an attribute and an element of the gamma_w Sequential (gotennet.py:277-292): the oracle's state dict
+    holds it once, expand_aliases adds the position-dependent `gamma_w.k.*` duplicates and needs the config for that."""
+    cfg = orc.OracleConfig(n_atom_basis=32, n_interactions=2, lmax=1, num_heads=4, edge_updates="linwa_ln_gated", evec_dim=16)
+    sd = orc.make_state_dict(cfg, seed=1)
+    assert sd["gata_list.0.W_edp.weight"].shape == (32, 16) and sd["gata_list.0.W_vq.weight"].shape == (16, 32)
+    with pytest.raises(ValueError):
+        orc.expand_aliases(sd)
+    full = orc.expand_aliases(sd, cfg)
+    # LayerNorm at 0, the activation at 1, W_edp at 2
+    assert full["gata_list.0.gamma_w.2.weight"] is sd["gata_list.0.W_edp.weight"]
+    assert "gata_list.0.gamma_w.0.weight" in full and "gata_list.1.W_edp.weight" not in full   # last layer has no HTR
+    assert orc.edge_lin_flags(cfg) == (2, 1)
+
+
 def test_constructor_errors(g):
     with pytest.raises(ValueError):
         g.GotenNet()  # cutoff_fn is mandatory (the reference dies with AttributeError, gotennet.py:839)
