@@ -803,7 +803,13 @@ static Tc16Plan tc16_plan(int M, int N, int K, int trans_a, int trans_b) {
   // it in place (no pre-split copy through HBM).  With several M tiles the kernel is shared-memory-bandwidth bound and
   // re-converting B per M tile costs more than the one pre-split pass (measured: 1792 x 256 x 301k, 0.94 -> 1.00 ms).
   // Needs one tile column per converter thread (BNH <= 128) and a TMA-addressable B (checked at launch).
-  t.b_raw = t.a_rows_are_k && t.n_mt <= 2 && t.block_n / t.ncta <= 128;
+  // GOTEN_GEMM_BRAW_MT: largest number of M tiles for which B is converted in the kernel.  Was 2 with four converter
+  // warps (1792 x 256 x 301k: 0.94 -> 1.00 ms with B re-converted per M tile); with eight converter warps the in-kernel
+  // form wins on every weight-gradient shape of the model (997 -> 850, 854 -> 710, 58.9 -> 52.9, 56.7 -> 51.1 us) and
+  // the pre-split pass over the activation-sized B operand (0.1 ms and 0.6 GB of traffic per edge weight gradient) goes
+  static int braw_mt = -1;
+  if (braw_mt < 0) { const char* e = getenv("GOTEN_GEMM_BRAW_MT"); braw_mt = e ? atoi(e) : 16; }
+  t.b_raw = t.a_rows_are_k && t.n_mt <= braw_mt && t.block_n / t.ncta <= 128;
   t.b_bytes = align256((int64_t)N * t.kp * 2);
   t.ws_bytes = 256 + 2 * t.b_bytes;
   if (t.splits > 1) t.ws_bytes += align256((int64_t)t.splits * ((int64_t)M * N + M) * 4);
